@@ -1,0 +1,271 @@
+"""Drop-in mirror of the reference's Mamba modules, running on the sm_100a kernels of libmamba_b200.so.
+
+Same class names, constructor arguments, parameter names/shapes (hence state_dict layout) and call
+signatures as the reference:
+  * `ModelArgs`, `Mamba(params)`, `ResidualBlock`, `MambaBlock`, `RMSNorm` — the pure-PyTorch Mamba-1 of
+    models/mamba/__pycache__/simple_mamba.cpython-311.pyc (source deleted upstream; SURVEY.md Appendix A;
+    `@Lnnn` = original source line).  "Layout P": keys embedding / metadata_embedding /
+    layers.{i}.mixer.* / layers.{i}.norm.weight / norm_f.weight / lm_head.weight (tied).
+  * `Mamba(d_model=1024, n_layers=10)` — the shipped wrapper's signature (models/mamba/mamba.py:8-35):
+    keys token_embedding / metadata_embedding / output_layer / layers.{i}.* / norm; no residuals, final
+    LayerNorm, untied head with bias.  Its layers here are `MambaBlock`s (the Mamba-1 maths that
+    BASELINE.json's north_star names); the external mamba_ssm.Mamba2 it stacks upstream is out of scope.
+Both forms take `forward(tokens[B,T] long, meta[B,6] long)` and return logits `[B, T, V]` (first 6
+positions dropped, mamba.py:35 / simple_mamba @L96).
+
+What runs where: conv1d+SiLU, softplus(dt)+scan+D-skip+z-gate, RMSNorm(+residual) and the decode step are
+this repo's CUDA kernels (ops.py -> C-ABI).  in_proj / x_proj / dt_proj / out_proj / lm_head are plain
+`F.linear` (cuBLAS; bf16 under `torch.autocast`), embeddings and `cat` are torch.  There is NO CPU path:
+calling a module on CPU tensors raises.
+
+Not in the reference (F3): `MambaBlock.step`, `Mamba.allocate_inference_cache / prefill / step` — the
+recurrent decode that replaces the full re-forward per token of scripts/generate.py:26-31.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from types import SimpleNamespace
+from typing import Union
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ... import ops
+from ...configs import common as cc
+from ...configs import mamba as cm
+
+__all__ = ["ModelArgs", "Mamba", "ResidualBlock", "MambaBlock", "RMSNorm"]
+
+
+@dataclass
+class ModelArgs:  # simple_mamba @L33-54
+    d_model: int
+    n_layer: int
+    vocab_size: int
+    d_state: int = 16
+    expand: int = 2
+    dt_rank: Union[int, str] = "auto"
+    d_conv: int = 4
+    pad_vocab_size_multiple: int = 8
+    conv_bias: bool = True
+    bias: bool = False
+    metadata_vocab_size: int = cc.metadata_vocab_size
+
+    def __post_init__(self):
+        self.d_inner = int(self.expand * self.d_model)
+        if self.dt_rank == "auto":
+            self.dt_rank = math.ceil(self.d_model / 16)
+        if self.vocab_size % self.pad_vocab_size_multiple != 0:
+            self.vocab_size += self.pad_vocab_size_multiple - self.vocab_size % self.pad_vocab_size_multiple
+
+
+def _act_dtype(x: torch.Tensor) -> torch.dtype:
+    """dtype the mixer runs in: the autocast dtype when autocast is on (fp32 residual stream, bf16 mixer),
+    else the tensor's own dtype."""
+    if torch.is_autocast_enabled("cuda"):
+        return torch.get_autocast_dtype("cuda")
+    return x.dtype
+
+
+class RMSNorm(nn.Module):  # simple_mamba @L336-348
+    def __init__(self, d_model: int, eps: float = 1e-5):
+        super().__init__()
+        self.eps = eps
+        self.weight = nn.Parameter(torch.ones(d_model))
+
+    def forward(self, x, residual=None):
+        """`forward(x)` is the reference call (@L346).  `forward(x, residual)` is the fused form used inside
+        Mamba.forward: returns (rmsnorm(x + residual), x + residual)."""
+        if residual is None:
+            return ops.rmsnorm_fn(x, self.weight, None, self.eps)[0]
+        return ops.rmsnorm_fn(x, self.weight, residual, self.eps, _act_dtype(residual))
+
+
+class MambaBlock(nn.Module):  # simple_mamba @L184
+    def __init__(self, params, layer_idx=None):  # @L185-211
+        super().__init__()
+        self.params = params
+        self.layer_idx = layer_idx
+        self.in_proj = nn.Linear(params.d_model, params.d_inner * 2, bias=params.bias)
+        self.conv1d = nn.Conv1d(in_channels=params.d_inner, out_channels=params.d_inner, bias=params.conv_bias,
+                                kernel_size=params.d_conv, groups=params.d_inner, padding=params.d_conv - 1)
+        self.x_proj = nn.Linear(params.d_inner, params.dt_rank + params.d_state * 2, bias=False)
+        self.dt_proj = nn.Linear(params.dt_rank, params.d_inner, bias=True)
+        A = torch.arange(1, params.d_state + 1, dtype=torch.float32).repeat(params.d_inner, 1)
+        self.A_log = nn.Parameter(torch.log(A))
+        self.D = nn.Parameter(torch.ones(params.d_inner))
+        self.out_proj = nn.Linear(params.d_inner, params.d_model, bias=params.bias)
+
+    # ---- training / full-sequence forward (@L228-245 with ssm @L263-280 and selective_scan @L310-333) --
+    def forward(self, x):
+        p = self.params
+        xz = self.in_proj(x)                                              # @L230  [B, L, 2*d_inner]
+        xs, res = xz.split([p.d_inner, p.d_inner], dim=-1)                # @L231  views, no copy
+        xc = ops.causal_conv1d_silu_fn(xs, self.conv1d.weight, self.conv1d.bias)   # @L233-237 (one kernel)
+        A = -torch.exp(self.A_log.float())                                # @L270
+        x_dbl = self.x_proj(xc)                                           # @L273
+        dt_r, Bm, Cm = x_dbl.split([p.dt_rank, p.d_state, p.d_state], dim=-1)  # @L275 views
+        dt_raw = F.linear(dt_r, self.dt_proj.weight)                      # @L276: bias + softplus fused below
+        y = ops.selective_scan_fn(xc, dt_raw, A, Bm, Cm, self.D.float(), z=res,
+                                  delta_bias=self.dt_proj.bias.float(), delta_softplus=True)  # @L276-278, @L241
+        return self.out_proj(y)                                           # @L243
+
+    # ---- inference: full-sequence forward that also leaves the recurrent state behind ---------------
+    @torch.no_grad()
+    def prefill(self, x, conv_state, ssm_state):
+        p = self.params
+        xz = self.in_proj(x)
+        xs, res = xz.split([p.d_inner, p.d_inner], dim=-1)
+        xc, cs = ops.causal_conv1d_silu_prefill(xs, self.conv1d.weight, self.conv1d.bias)
+        conv_state.copy_(cs)
+        A = -torch.exp(self.A_log.float())
+        x_dbl = self.x_proj(xc)
+        dt_r, Bm, Cm = x_dbl.split([p.dt_rank, p.d_state, p.d_state], dim=-1)
+        dt_raw = F.linear(dt_r, self.dt_proj.weight)
+        y, h_last = ops.selective_scan_prefill(xc, dt_raw, A, Bm, Cm, self.D.float(), z=res,
+                                               delta_bias=self.dt_proj.bias.float(), delta_softplus=True)
+        ssm_state.copy_(h_last)
+        return self.out_proj(y)
+
+    def allocate_inference_cache(self, batch_size, max_seqlen=None, dtype=None, device=None):
+        """(conv_state [B, d_inner, d_conv], ssm_state [B, d_inner, d_state] fp32), zero-initialised —
+        the two tensors mamba_ssm's `allocate_inference_cache` hands out (used in the reference's
+        scripts/test_inference.ipynb:137)."""
+        p = self.params
+        device = device or self.in_proj.weight.device
+        dtype = dtype or self.in_proj.weight.dtype
+        conv_state = torch.zeros(batch_size, p.d_inner, p.d_conv, device=device, dtype=dtype)
+        ssm_state = torch.zeros(batch_size, p.d_inner, p.d_state, device=device, dtype=torch.float32)
+        return conv_state, ssm_state
+
+    @torch.no_grad()
+    def step(self, x_t, conv_state, ssm_state):
+        """One new position: x_t [B, d_model] -> [B, d_model]; both states are updated in place."""
+        p = self.params
+        xz = self.in_proj(x_t)                                            # [B, 2*d_inner]
+        xs, res = xz.split([p.d_inner, p.d_inner], dim=-1)
+        w2 = self.conv1d.weight.detach().float().view(p.d_inner, p.d_conv)
+        cb = None if self.conv1d.bias is None else self.conv1d.bias.detach().float()
+        T = conv_state.dtype                                              # the step's activation dtype
+        xc = ops.conv_step(xs.to(T), conv_state, w2, cb)
+        A = -torch.exp(self.A_log.float())
+        x_dbl = self.x_proj(xc).to(T)
+        dt_r, Bv, Cv = x_dbl.split([p.dt_rank, p.d_state, p.d_state], dim=-1)
+        y = ops.ssm_step(xc, dt_r, Bv, Cv, self.dt_proj.weight.detach().float().contiguous(),
+                         self.dt_proj.bias.detach().float(), A, self.D.detach().float(), res.to(T), ssm_state)
+        return self.out_proj(y)
+
+
+class ResidualBlock(nn.Module):  # simple_mamba @L151-181
+    def __init__(self, params, layer_idx=None):
+        super().__init__()
+        self.params = params
+        self.mixer = MambaBlock(params, layer_idx)
+        self.norm = RMSNorm(params.d_model)
+
+    def forward(self, x):  # @L179
+        return self.mixer(self.norm(x)) + x
+
+
+def _params_from_configs(d_model=None, n_layers=None, vocab_size=None, pad=False):
+    mv = cm.config.model_values
+    d_model = mv.d_model if d_model is None else d_model
+    return ModelArgs(d_model=d_model, n_layer=mv.n_layer if n_layers is None else n_layers,
+                     vocab_size=cc.vocab_size if vocab_size is None else vocab_size, d_state=mv.d_state,
+                     expand=mv.expand, d_conv=mv.d_conv, conv_bias=mv.conv_bias, bias=mv.bias,
+                     pad_vocab_size_multiple=mv.pad_vocab_size_multiple if pad else 1,
+                     metadata_vocab_size=cc.metadata_vocab_size)
+
+
+class Mamba(nn.Module):
+    """`Mamba(params)` -> Layout P (simple_mamba @L57-96);  `Mamba()` / `Mamba(d_model=1024, n_layers=10)` ->
+    the shipped wrapper's layout (models/mamba/mamba.py:8-35)."""
+
+    def __init__(self, d_model: Union[int, SimpleNamespace, ModelArgs] = 1024, n_layers: int = 10):
+        super().__init__()
+        if isinstance(d_model, int):
+            self.layout = "S"
+            params = _params_from_configs(d_model, n_layers)
+            self.params = params
+            self.token_embedding = nn.Embedding(cc.vocab_size, d_model)            # mamba.py:12
+            self.metadata_embedding = nn.Embedding(cc.metadata_vocab_size, d_model)  # :13
+            self.output_layer = nn.Linear(d_model, cc.vocab_size)                  # :14
+            self.layers = nn.ModuleList([MambaBlock(params, layer_idx=i) for i in range(n_layers)])  # :16-24
+            self.norm = nn.LayerNorm(d_model)                                      # :25
+        else:
+            self.layout = "P"
+            params = d_model
+            self.params = params
+            self.vocab_size = params.vocab_size
+            self.metadata_vocab_size = params.metadata_vocab_size
+            self.embedding = nn.Embedding(params.vocab_size, params.d_model)       # @L62
+            self.metadata_embedding = nn.Embedding(params.metadata_vocab_size, params.d_model)
+            self.layers = nn.ModuleList([ResidualBlock(params, layer_idx=i) for i in range(params.n_layer)])
+            self.norm_f = RMSNorm(params.d_model)
+            self.lm_head = nn.Linear(params.d_model, params.vocab_size, bias=False)
+            self.lm_head.weight = self.embedding.weight                            # tied, @L70
+
+    def get_name(self):  # @L147
+        return "Mamba"
+
+    # ---- embeddings (both layouts): cat((meta_emb, token_emb), dim=-2) --------------------------------
+    def _embed(self, tokens, meta):
+        tok = self.embedding if self.layout == "P" else self.token_embedding
+        return torch.cat((self.metadata_embedding(meta), tok(tokens)), dim=-2)
+
+    def forward(self, tokens, meta):
+        x = self._embed(tokens, meta)
+        n_meta = meta.shape[-1]
+        if self.layout == "S":  # mamba.py:32-35
+            for layer in self.layers:
+                x = layer(x)
+            x = self.norm(x)
+            return self.output_layer(x[:, n_meta:])
+        # Layout P, @L90-96.  `mixer(norm(x)) + x` per layer, with each `+ x` fused into the next RMSNorm:
+        # the residual stream is read and written once per layer.
+        resid, hidden = x, None
+        for layer in self.layers:
+            normed, resid = layer.norm(hidden, resid)
+            hidden = layer.mixer(normed)
+        normed, _ = self.norm_f(hidden, resid)
+        return self.lm_head(normed[:, n_meta:])  # rows are independent: slicing before the GEMM == logits[:, 6:]
+
+    # ---- recurrent decode (no reference counterpart) -------------------------
+    def allocate_inference_cache(self, batch_size, max_seqlen=None, dtype=None):
+        mixers = [l.mixer if self.layout == "P" else l for l in self.layers]
+        return [m.allocate_inference_cache(batch_size, max_seqlen, dtype) for m in mixers]
+
+    @torch.no_grad()
+    def prefill(self, tokens, meta, cache):
+        """Full forward over the prompt that leaves (conv_state, ssm_state) of every layer in `cache`.
+        Returns logits [B, T, V] exactly as forward()."""
+        x = self._embed(tokens, meta)
+        n_meta = meta.shape[-1]
+        if self.layout == "S":
+            for layer, (cs, hs) in zip(self.layers, cache):
+                x = layer.prefill(x, cs, hs)
+            return self.output_layer(self.norm(x)[:, n_meta:])
+        resid, hidden = x, None
+        for layer, (cs, hs) in zip(self.layers, cache):
+            normed, resid = layer.norm(hidden, resid)
+            hidden = layer.mixer.prefill(normed, cs, hs)
+        normed, _ = self.norm_f(hidden, resid)
+        return self.lm_head(normed[:, n_meta:])
+
+    @torch.no_grad()
+    def step(self, token, cache):
+        """token [B] long -> logits [B, V]; advances every layer's state by one position."""
+        tok = self.embedding if self.layout == "P" else self.token_embedding
+        x = tok(token)
+        if self.layout == "S":
+            for layer, (cs, hs) in zip(self.layers, cache):
+                x = layer.step(x, cs, hs)
+            return self.output_layer(self.norm(x))
+        resid, hidden = x, None
+        for layer, (cs, hs) in zip(self.layers, cache):
+            normed, resid = layer.norm(hidden, resid)
+            hidden = layer.mixer.step(normed, cs, hs)
+        normed, _ = self.norm_f(hidden, resid)
+        return self.lm_head(normed)

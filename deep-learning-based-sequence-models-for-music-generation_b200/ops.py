@@ -1,0 +1,425 @@
+"""torch.autograd.Function wrappers over the C-ABI (include/mamba_b200.h).
+
+PyTorch is plumbing here: it owns device memory, the current stream and autograd bookkeeping; all
+arithmetic of the hot path runs in libmamba_b200.so.  Nothing in this module computes on the CPU
+and nothing falls back to torch ops: a missing library or a non-CUDA tensor raises.
+
+Reference behaviour replaced (models/mamba/__pycache__/simple_mamba.cpython-311.pyc, see SURVEY.md
+Appendix A):  selective_scan_fn -> MambaBlock.selective_scan @L310-333 (+ softplus @L276, D skip
+@L331, gate @L241);  causal_conv1d_silu_fn -> @L233-237;  rmsnorm_fn -> RMSNorm.forward @L346 and
+the residual add of ResidualBlock.forward @L179;  conv_step / ssm_step -> the same maths for one
+new token (no reference counterpart: scripts/generate.py:26-31 re-runs the full model).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+from . import _lib
+from ._lib import (FLAG_DELTA_SOFTPLUS, FLAG_HAS_D, FLAG_HAS_DELTA_BIAS, FLAG_HAS_Z, MAMBA_BF16, MAMBA_F32, ConvArgs,
+                   NormArgs, ScanBwdArgs, ScanFwdArgs, StepArgs, check, lib)
+
+_DTYPES = {torch.float32: MAMBA_F32, torch.bfloat16: MAMBA_BF16}
+
+# tuning knobs (0 = library default); exposed for the kernel sweeps in bench.py
+SCAN_CHUNK = int(os.environ.get("MAMBA_B200_SCAN_CHUNK", "16"))
+SCAN_FWD_VARIANT = int(os.environ.get("MAMBA_B200_FWD_VARIANT", "0"))
+SCAN_BWD_VARIANT = int(os.environ.get("MAMBA_B200_BWD_VARIANT", "0"))
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(
+                "mamba_b200 ops run only on CUDA tensors (sm_100a kernels); there is no CPU fallback — "
+                f"got a tensor on {t.device}")
+
+
+def _dtype_code(t: torch.Tensor) -> int:
+    try:
+        return _DTYPES[t.dtype]
+    except KeyError:
+        raise TypeError(f"mamba_b200: unsupported activation dtype {t.dtype} (float32 or bfloat16)") from None
+
+
+def _rows(t: torch.Tensor) -> torch.Tensor:
+    """[B, L, X] tensor with unit stride on the last axis (views of split() stay views)."""
+    return t if t.stride(-1) == 1 else t.contiguous()
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32(t):
+    if t is None:
+        return None
+    return t.detach().to(torch.float32).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# selective scan
+# ------------------------------------------------------------------------------------------------
+def _scan_fwd_raw(u, delta, A, B, C, D, z, delta_bias, delta_softplus, ckpt, chunk, h_init=None, h_last=None,
+                  variant=0):
+    Bsz, L, Dm = u.shape
+    N = A.shape[1]
+    out = torch.empty((Bsz, L, Dm), dtype=u.dtype, device=u.device)
+    a = ScanFwdArgs()
+    a.struct_size = C.sizeof(ScanFwdArgs)
+    a.dtype = _dtype_code(u)
+    a.batch, a.seqlen, a.dim, a.dstate = Bsz, L, Dm, N
+    a.chunk = chunk
+    a.flags = ((FLAG_HAS_Z if z is not None else 0) | (FLAG_DELTA_SOFTPLUS if delta_softplus else 0)
+               | (FLAG_HAS_DELTA_BIAS if delta_bias is not None else 0) | (FLAG_HAS_D if D is not None else 0))
+    a.variant = variant
+    a.u, a.u_bs, a.u_ls = _p(u), u.stride(0), u.stride(1)
+    a.delta, a.delta_bs, a.delta_ls = _p(delta), delta.stride(0), delta.stride(1)
+    a.A = _p(A)
+    a.B, a.B_bs, a.B_ls = _p(B), B.stride(0), B.stride(1)
+    a.C, a.C_bs, a.C_ls = _p(C), C.stride(0), C.stride(1)
+    a.D = _p(D)
+    if z is not None:
+        a.z, a.z_bs, a.z_ls = _p(z), z.stride(0), z.stride(1)
+    a.delta_bias = _p(delta_bias)
+    a.out, a.out_bs, a.out_ls = _p(out), out.stride(0), out.stride(1)
+    a.ckpt = _p(ckpt)
+    a.h_last = _p(h_last)
+    a.h_init = _p(h_init)
+    with torch.cuda.device(u.device):
+        check(lib().mamba_scan_fwd(C.byref(a), _stream()), "mamba_scan_fwd")
+    return out
+
+
+class SelectiveScanFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, u, delta, A, B, C, D, z, delta_bias, delta_softplus, chunk):
+        _require_cuda(u, delta, A, B, C, D, z, delta_bias)
+        if u.dim() != 3 or delta.shape != u.shape:
+            raise ValueError(f"selective_scan: u {tuple(u.shape)} and delta {tuple(delta.shape)} must be equal [B, L, D]")
+        if A.dim() != 2 or A.shape[0] != u.shape[2]:
+            raise ValueError(f"selective_scan: A {tuple(A.shape)} must be [D={u.shape[2]}, N]")
+        if B.shape != (u.shape[0], u.shape[1], A.shape[1]) or C.shape != B.shape:
+            raise ValueError(f"selective_scan: B {tuple(B.shape)} / C {tuple(C.shape)} must be [B, L, N]")
+        dt = u.dtype
+        _dtype_code(u)
+        u, delta, B, C = (_rows(t.to(dt)) for t in (u, delta, B, C))
+        z = None if z is None else _rows(z.to(dt))
+        A32, D32, b32 = _f32(A), _f32(D), _f32(delta_bias)
+        need_grad = any(ctx.needs_input_grad[:8])
+        ckpt = None
+        if need_grad and u.shape[1] > chunk:
+            n = lib().mamba_scan_ckpt_elems(u.shape[0], u.shape[1], u.shape[2], A.shape[1], chunk)
+            ckpt = torch.empty(n, dtype=torch.float32, device=u.device)
+        out = _scan_fwd_raw(u, delta, A32, B, C, D32, z, b32, delta_softplus, ckpt, chunk, variant=SCAN_FWD_VARIANT)
+        ctx.save_for_backward(u, delta, A32, B, C, D32, z, b32, ckpt)
+        ctx.delta_softplus = delta_softplus
+        ctx.chunk = chunk
+        ctx.in_dtypes = (A.dtype, None if D is None else D.dtype, None if delta_bias is None else delta_bias.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        u, delta, A, B, C, D, z, dbias, ckpt = ctx.saved_tensors
+        Bsz, L, Dm = u.shape
+        N = A.shape[1]
+        dout = _rows(dout.to(u.dtype))
+        dev = u.device
+        du = torch.empty_like(u, memory_format=torch.contiguous_format)
+        ddelta = torch.empty((Bsz, L, Dm), dtype=u.dtype, device=dev)
+        dz = torch.empty((Bsz, L, Dm), dtype=u.dtype, device=dev) if z is not None else None
+        dB = torch.empty((Bsz, L, N), dtype=u.dtype, device=dev)
+        dC = torch.empty((Bsz, L, N), dtype=u.dtype, device=dev)
+        dA = torch.empty((Dm, N), dtype=torch.float32, device=dev)
+        dD = torch.empty((Dm,), dtype=torch.float32, device=dev) if D is not None else None
+        ddb = torch.empty((Dm,), dtype=torch.float32, device=dev) if dbias is not None else None
+        wsb = lib().mamba_scan_bwd_workspace_bytes(Bsz, L, Dm, N)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        a = ScanBwdArgs()
+        a.struct_size = C_sizeof(ScanBwdArgs)
+        a.dtype = _dtype_code(u)
+        a.batch, a.seqlen, a.dim, a.dstate = Bsz, L, Dm, N
+        a.chunk = ctx.chunk
+        a.flags = ((FLAG_HAS_Z if z is not None else 0) | (FLAG_DELTA_SOFTPLUS if ctx.delta_softplus else 0)
+                   | (FLAG_HAS_DELTA_BIAS if dbias is not None else 0) | (FLAG_HAS_D if D is not None else 0))
+        a.variant = SCAN_BWD_VARIANT
+        a.u, a.u_bs, a.u_ls = _p(u), u.stride(0), u.stride(1)
+        a.delta, a.delta_bs, a.delta_ls = _p(delta), delta.stride(0), delta.stride(1)
+        a.A = _p(A)
+        a.B, a.B_bs, a.B_ls = _p(B), B.stride(0), B.stride(1)
+        a.C, a.C_bs, a.C_ls = _p(C), C.stride(0), C.stride(1)
+        a.D = _p(D)
+        if z is not None:
+            a.z, a.z_bs, a.z_ls = _p(z), z.stride(0), z.stride(1)
+            a.dz, a.dz_bs, a.dz_ls = _p(dz), dz.stride(0), dz.stride(1)
+        a.delta_bias = _p(dbias)
+        a.dout, a.dout_bs, a.dout_ls = _p(dout), dout.stride(0), dout.stride(1)
+        a.ckpt = _p(ckpt)
+        a.du, a.du_bs, a.du_ls = _p(du), du.stride(0), du.stride(1)
+        a.ddelta, a.ddelta_bs, a.ddelta_ls = _p(ddelta), ddelta.stride(0), ddelta.stride(1)
+        a.dB, a.dB_bs, a.dB_ls = _p(dB), dB.stride(0), dB.stride(1)
+        a.dC, a.dC_bs, a.dC_ls = _p(dC), dC.stride(0), dC.stride(1)
+        a.dA, a.dD, a.ddelta_bias = _p(dA), _p(dD), _p(ddb)
+        a.workspace, a.workspace_bytes = _p(ws), wsb
+        with torch.cuda.device(dev):
+            check(lib().mamba_scan_bwd(C.byref(a), _stream()), "mamba_scan_bwd")
+        tA, tD, tb = ctx.in_dtypes
+        return (du, ddelta, dA.to(tA), dB, dC, None if dD is None else dD.to(tD), dz,
+                None if ddb is None else ddb.to(tb), None, None)
+
+
+C_sizeof = C.sizeof
+
+
+def selective_scan_fn(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus=False, chunk=None):
+    """Fused selective scan.  u, delta: [B, L, D]; A: [D, N]; B, C: [B, L, N]; D, delta_bias: [D];
+    z: [B, L, D].  Returns out [B, L, D] = (scan(u, delta, A, B, C) + D*u) * silu(z)."""
+    return SelectiveScanFn.apply(u, delta, A, B, C, D, z, delta_bias, bool(delta_softplus),
+                                 SCAN_CHUNK if chunk is None else int(chunk))
+
+
+def selective_scan_prefill(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus=False, h_init=None):
+    """Inference-only scan that also returns the final state h_{L-1} ([B, D, N] fp32) for decode."""
+    _require_cuda(u, delta, A, B, C)
+    dt = u.dtype
+    u, delta, B, C = (_rows(t.to(dt)) for t in (u, delta, B, C))
+    z = None if z is None else _rows(z.to(dt))
+    h_last = torch.empty((u.shape[0], u.shape[2], A.shape[1]), dtype=torch.float32, device=u.device)
+    out = _scan_fwd_raw(u, delta, _f32(A), B, C, _f32(D), z, _f32(delta_bias), delta_softplus, None, 16,
+                        h_init=None if h_init is None else h_init.contiguous(), h_last=h_last,
+                        variant=SCAN_FWD_VARIANT)
+    return out, h_last
+
+
+# ------------------------------------------------------------------------------------------------
+# causal depthwise conv1d + SiLU
+# ------------------------------------------------------------------------------------------------
+def _conv_args(x, w2, bias, K):
+    a = ConvArgs()
+    a.struct_size = C.sizeof(ConvArgs)
+    a.dtype = _dtype_code(x)
+    a.batch, a.seqlen, a.dim, a.width = x.shape[0], x.shape[1], x.shape[2], K
+    a.x, a.x_bs, a.x_ls = _p(x), x.stride(0), x.stride(1)
+    a.weight, a.bias = _p(w2), _p(bias)
+    return a
+
+
+class CausalConv1dSiluFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        _require_cuda(x, weight, bias)
+        D = x.shape[2]
+        K = weight.shape[-1]
+        if weight.numel() != D * K:
+            raise ValueError(f"causal_conv1d: weight {tuple(weight.shape)} must be depthwise [D={D}, 1, K]")
+        x = _rows(x)
+        w2 = _f32(weight).view(D, K)
+        b32 = _f32(bias)
+        out = torch.empty((x.shape[0], x.shape[1], D), dtype=x.dtype, device=x.device)
+        a = _conv_args(x, w2, b32, K)
+        a.out, a.out_bs, a.out_ls = _p(out), out.stride(0), out.stride(1)
+        with torch.cuda.device(x.device):
+            check(lib().mamba_conv1d_silu_fwd(C.byref(a), _stream()), "mamba_conv1d_silu_fwd")
+        ctx.save_for_backward(x, w2, b32)
+        ctx.wshape = weight.shape
+        ctx.wdtype = weight.dtype
+        ctx.bdtype = None if bias is None else bias.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, w2, b32 = ctx.saved_tensors
+        Bsz, L, D = x.shape
+        K = w2.shape[1]
+        dout = _rows(dout.to(x.dtype))
+        dx = torch.empty((Bsz, L, D), dtype=x.dtype, device=x.device)
+        dw = torch.empty((D, K), dtype=torch.float32, device=x.device)
+        db = torch.empty((D,), dtype=torch.float32, device=x.device) if b32 is not None else None
+        wsb = lib().mamba_conv1d_bwd_workspace_bytes(Bsz, L, D, K)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=x.device)
+        a = _conv_args(x, w2, b32, K)
+        a.dout, a.dout_bs, a.dout_ls = _p(dout), dout.stride(0), dout.stride(1)
+        a.dx, a.dx_bs, a.dx_ls = _p(dx), dx.stride(0), dx.stride(1)
+        a.dweight, a.dbias = _p(dw), _p(db)
+        a.workspace, a.workspace_bytes = _p(ws), wsb
+        with torch.cuda.device(x.device):
+            check(lib().mamba_conv1d_silu_bwd(C.byref(a), _stream()), "mamba_conv1d_silu_bwd")
+        return dx, dw.view(ctx.wshape).to(ctx.wdtype), None if db is None else db.to(ctx.bdtype)
+
+
+def causal_conv1d_silu_fn(x, weight, bias=None):
+    """silu(depthwise causal conv1d(x)) for x [B, L, D] (channels last); weight [D, 1, K] or [D, K]."""
+    return CausalConv1dSiluFn.apply(x, weight, bias)
+
+
+def causal_conv1d_silu_prefill(x, weight, bias=None):
+    """Inference-only conv that also returns conv_state [B, D, K] (the last K inputs per channel)."""
+    _require_cuda(x, weight, bias)
+    x = _rows(x)
+    D, K = x.shape[2], weight.shape[-1]
+    w2, b32 = _f32(weight).view(D, K), _f32(bias)
+    out = torch.empty((x.shape[0], x.shape[1], D), dtype=x.dtype, device=x.device)
+    state = torch.empty((x.shape[0], D, K), dtype=x.dtype, device=x.device)
+    a = _conv_args(x, w2, b32, K)
+    a.out, a.out_bs, a.out_ls = _p(out), out.stride(0), out.stride(1)
+    a.final_state = _p(state)
+    with torch.cuda.device(x.device):
+        check(lib().mamba_conv1d_silu_fwd(C.byref(a), _stream()), "mamba_conv1d_silu_fwd")
+    return out, state
+
+
+# ------------------------------------------------------------------------------------------------
+# RMSNorm (+ residual add)
+# ------------------------------------------------------------------------------------------------
+def _norm_args(act_dtype, resid_dtype, rows, dim, eps):
+    a = NormArgs()
+    a.struct_size = C.sizeof(NormArgs)
+    a.dtype = _DTYPES[act_dtype]
+    a.resid_dtype = _DTYPES[resid_dtype]
+    a.rows, a.dim, a.eps = rows, dim, eps
+    return a
+
+
+class RMSNormFn(torch.autograd.Function):
+    """(x [T] | None, weight, residual [TR] | None) -> (y [T], x + residual [TR]).  T = act_dtype."""
+
+    @staticmethod
+    def forward(ctx, x, weight, residual, eps, act_dtype):
+        _require_cuda(x, weight, residual)
+        ref = x if x is not None else residual
+        if ref is None:
+            raise ValueError("rmsnorm: x and residual are both None")
+        shape, dim, dev = ref.shape, ref.shape[-1], ref.device
+        T = act_dtype if act_dtype is not None else (x.dtype if x is not None else residual.dtype)
+        TR = residual.dtype if residual is not None else T
+        if T not in _DTYPES or TR not in _DTYPES:
+            raise TypeError(f"rmsnorm: unsupported dtypes ({T}, {TR})")
+        x2 = None if x is None else x.to(T).reshape(-1, dim).contiguous()
+        r2 = None if residual is None else residual.reshape(-1, dim).contiguous()
+        w32 = _f32(weight)
+        rows = (x2 if x2 is not None else r2).shape[0]
+        y = torch.empty((rows, dim), dtype=T, device=dev)
+        # the summed stream is materialised only when there is a sum; otherwise it IS the one operand
+        ro = torch.empty((rows, dim), dtype=TR, device=dev) if (x2 is not None and r2 is not None) else None
+        rstd = torch.empty((rows,), dtype=torch.float32, device=dev)
+        a = _norm_args(T, TR, rows, dim, eps)
+        a.x, a.residual, a.weight = _p(x2), _p(r2), _p(w32)
+        a.y, a.resid_out, a.rstd = _p(y), _p(ro), _p(rstd)
+        with torch.cuda.device(dev):
+            check(lib().mamba_rmsnorm_fwd(C.byref(a), _stream()), "mamba_rmsnorm_fwd")
+        normed = ro if ro is not None else (r2 if r2 is not None else x2)
+        ctx.save_for_backward(normed, w32, rstd)
+        ctx.meta = (T, TR, eps, shape, weight.dtype, x is not None, residual is not None)
+        # with a single operand the stream IS that operand: rmsnorm_fn hands the input itself back so that
+        # autograd sees the aliasing (returning a view from here would cut the gradient)
+        return y.view(shape), (None if ro is None else ro.view(shape))
+
+    @staticmethod
+    def backward(ctx, dy, dres):
+        normed, w32, rstd = ctx.saved_tensors
+        T, TR, eps, shape, wdtype, has_x, has_res = ctx.meta
+        rows, dim = normed.shape
+        dev = normed.device
+        NT = normed.dtype  # dtype of the tensor that was normalised
+        dy2 = dy.to(T).reshape(-1, dim).contiguous()
+        both = has_x and has_res
+        dr2 = None if (dres is None or not both) else dres.to(TR).reshape(-1, dim).contiguous()
+        dx = torch.empty((rows, dim), dtype=T, device=dev) if has_x else None
+        dro = torch.empty((rows, dim), dtype=TR, device=dev) if has_res and (not has_x or TR != T) else None
+        dw = torch.empty((dim,), dtype=torch.float32, device=dev)
+        wsb = lib().mamba_rmsnorm_bwd_workspace_bytes(rows, dim)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        a = _norm_args(T, NT, rows, dim, eps)
+        a.residual, a.weight, a.rstd = _p(normed), _p(w32), _p(rstd)
+        a.dy, a.dresid_in, a.dweight = _p(dy2), _p(dr2), _p(dw)
+        if NT == T:
+            a.dx = _p(dx if dx is not None else dro)
+            if dx is not None and dro is not None:
+                a.dresid_out = _p(dro)
+        else:
+            a.dx, a.dresid_out = _p(dx), _p(dro)
+        a.workspace, a.workspace_bytes = _p(ws), wsb
+        with torch.cuda.device(dev):
+            check(lib().mamba_rmsnorm_bwd(C.byref(a), _stream()), "mamba_rmsnorm_bwd")
+        gx = dx.view(shape) if has_x else None
+        if has_res:
+            gr = (dro if dro is not None else dx).view(shape)
+        else:
+            gr = None
+        return gx, dw.to(wdtype), gr, None, None
+
+
+def rmsnorm_fn(x, weight, residual=None, eps=1e-5, act_dtype=None):
+    """y = rmsnorm(x + residual) * weight.  Returns (y, stream) where stream = x + residual in the
+    residual's dtype (or the single operand itself when only one of x / residual is given).
+    `act_dtype` is the dtype of y (default: x's, else residual's): the residual stream can stay fp32 while
+    the mixer runs in bf16."""
+    y, stream = RMSNormFn.apply(x, weight, residual, float(eps), act_dtype)
+    if stream is None:
+        stream = residual if residual is not None else x
+    return y, stream
+
+
+# ------------------------------------------------------------------------------------------------
+# decode step (no autograd)
+# ------------------------------------------------------------------------------------------------
+def _step_args(dtype_t, Bsz, D, N, K, R, flags):
+    a = StepArgs()
+    a.struct_size = C.sizeof(StepArgs)
+    a.dtype = _dtype_code(dtype_t)
+    a.batch, a.dim, a.dstate, a.width, a.dt_rank, a.flags = Bsz, D, N, K, R, flags
+    return a
+
+
+@torch.no_grad()
+def conv_step(x, conv_state, weight2d, bias):
+    """x [B, D] (row stride free), conv_state [B, D, K] updated in place -> xc [B, D]."""
+    _require_cuda(x, conv_state, weight2d, bias)
+    Bsz, D, K = conv_state.shape
+    if x.stride(-1) != 1 or not conv_state.is_contiguous():
+        raise ValueError("conv_step: x must have unit inner stride and conv_state must be contiguous")
+    xc = torch.empty((Bsz, D), dtype=x.dtype, device=x.device)
+    a = _step_args(x, Bsz, D, 0, K, 0, 0)
+    a.x, a.x_bs = _p(x), x.stride(0)
+    a.conv_state, a.conv_weight, a.conv_bias = _p(conv_state), _p(weight2d), _p(bias)
+    a.xc, a.xc_bs = _p(xc), xc.stride(0)
+    with torch.cuda.device(x.device):
+        check(lib().mamba_conv_step(C.byref(a), _stream()), "mamba_conv_step")
+    return xc
+
+
+@torch.no_grad()
+def ssm_step(xc, dt_in, Bv, Cv, dt_weight, dt_bias, A, D, z, ssm_state, delta_softplus=True):
+    """One recurrence step; ssm_state [B, D, N] fp32 updated in place -> y [B, D]."""
+    _require_cuda(xc, dt_in, Bv, Cv, dt_weight, dt_bias, A, D, z, ssm_state)
+    Bsz, Dm, N = ssm_state.shape
+    R = dt_in.shape[-1]
+    for t in (xc, dt_in, Bv, Cv, z):
+        if t is not None and t.stride(-1) != 1:
+            raise ValueError("ssm_step: activation tensors must have unit inner stride")
+    y = torch.empty((Bsz, Dm), dtype=xc.dtype, device=xc.device)
+    flags = ((FLAG_HAS_Z if z is not None else 0) | (FLAG_DELTA_SOFTPLUS if delta_softplus else 0)
+             | (FLAG_HAS_D if D is not None else 0))
+    a = _step_args(xc, Bsz, Dm, N, 0, R, flags)
+    a.xc, a.xc_bs = _p(xc), xc.stride(0)
+    a.dt_in, a.dt_in_bs = _p(dt_in), dt_in.stride(0)
+    a.Bv, a.Bv_bs = _p(Bv), Bv.stride(0)
+    a.Cv, a.Cv_bs = _p(Cv), Cv.stride(0)
+    a.dt_weight, a.dt_bias, a.A, a.D = _p(dt_weight), _p(dt_bias), _p(A), _p(D)
+    if z is not None:
+        a.z, a.z_bs = _p(z), z.stride(0)
+    a.ssm_state = _p(ssm_state)
+    a.y, a.y_bs = _p(y), y.stride(0)
+    with torch.cuda.device(xc.device):
+        check(lib().mamba_ssm_step(C.byref(a), _stream()), "mamba_ssm_step")
+    return y
+
+
+def launch_count() -> int:
+    return _lib.launch_count()

@@ -1,0 +1,196 @@
+"""Host-side mirror of the reference's train.py / train_parallel.py entry points for the Mamba path.
+
+Same function names and behaviour as the reference: `get_actual_vocab_size`, `get_mamba_dict`
+(train.py:21-36), `new_model` (:52-61), `make_distributions` (:79-111),
+`pick_distributions_by_prev_token` (:114-131), `filtered_logit` (:133-138).  The reference's epoch loop
+(:140-217) is I/O around one repeated step; `train_step` is that step (:160-169) and `Trainer` runs it
+as one CUDA graph (forward, loss, backward, gradient all-reduce, Adam) — the B200-native replacement for
+the python-launched loop.  Data loading, checkpoint naming and JSON logging stay the caller's.
+
+The loss is outside the scan/conv hot path but sits on the fwd+bwd step, so it is restated verbatim —
+including its quirk that `log_softmax` runs over dim=1, the SEQUENCE axis.
+"""
+from __future__ import annotations
+
+import math
+import os
+from types import SimpleNamespace
+
+import torch
+import torch.nn.functional as F
+
+from . import models
+from .configs import common as cc
+from .configs import mamba as cm
+
+
+def get_actual_vocab_size(type):  # train.py:21-26
+    config = cm.config.model_values
+    new_vocab_size = cc.vocab_size
+    if type == "mamba":
+        if new_vocab_size % config.pad_vocab_size_multiple != 0:
+            new_vocab_size += config.pad_vocab_size_multiple - new_vocab_size % config.pad_vocab_size_multiple
+    return new_vocab_size
+
+
+def get_mamba_dict(pad_vocab: bool = False):
+    """train.py:28-36.  The reference pads vocab_size to a multiple of 8 here (17914 -> 17920) and then
+    reshapes logits to cc.vocab_size columns in its loop (:162), which cannot both hold; like the shipped
+    wrapper (models/mamba/mamba.py:12-14) the default here is the unpadded vocabulary."""
+    mv = cm.config.model_values
+    config = SimpleNamespace(**vars(mv))
+    config.d_inner = int(config.expand * config.d_model)
+    config.dt_rank = math.ceil(config.d_model / 16)
+    config.vocab_size = get_actual_vocab_size("mamba") if pad_vocab else cc.vocab_size
+    config.metadata_vocab_size = cc.metadata_vocab_size
+    return SimpleNamespace(**vars(config), **vars(cc.config.values))
+
+
+def new_model(type="mamba", layout="P"):  # train.py:52-61
+    if type != "mamba":
+        raise ValueError("mamba_b200 provides the Mamba path only (xlstm / transformer are out of scope)")
+    if layout == "S":
+        return models.mamba.Mamba()              # the shipped call, train.py:54
+    return models.mamba.Mamba(get_mamba_dict())  # the pure-PyTorch model's call (train.cpython-313.pyc @L49)
+
+
+_dist_cache = {}
+
+
+def make_distributions(device=None):  # train.py:79-111
+    device = torch.device(cc.config.values.device if device is None else device)
+    key = str(device)
+    if key in _dist_cache:  # constant table: built once per device instead of once per call
+        return _dist_cache[key]
+    vocab_size = cc.vocab_size
+    distributions = torch.zeros(5, vocab_size, device=device)
+    s = cc.start_idx
+    start = [s["pitch"], s["dyn"], s["length"], s["time"], s["tempo"]]
+    end = [s["dyn"] - 1, s["length"] - 1, s["time"] - 1, s["tempo"] - 1, vocab_size]
+    for token in range(5):
+        distributions[token - 1, start[token]:end[token]] = 1
+    distributions[2, start[4]:end[4]] = 1
+    length_tensor = torch.linspace(1, 3, steps=cc.config.discretization.length - 1).to(device)  # train.py:20
+    distributions[1, s["length"]:s["time"] - 1] *= length_tensor
+    distributions[4, s["pitch"]:s["dyn"] - 1] *= 10
+    _dist_cache[key] = distributions
+    return distributions
+
+
+def pick_distributions_by_prev_token(input_tokens):  # train.py:114-131
+    s = cc.start_idx
+    boundaries = [s["dyn"] - 1, s["length"] - 1, s["time"] - 1, s["tempo"] - 1]
+    key = ("bins", str(input_tokens.device))
+    if key not in _dist_cache:
+        _dist_cache[key] = torch.tensor(boundaries, device=input_tokens.device)
+    buckets = torch.bucketize(input_tokens, _dist_cache[key], right=False)
+    return make_distributions(input_tokens.device)[buckets]
+
+
+def filtered_logit(input, output):  # train.py:133-138
+    weights = pick_distributions_by_prev_token(input)
+    log_probs = F.log_softmax(output.float(), dim=1)
+    return -log_probs * weights
+
+
+def loss_fn(src, trg, output):  # train.py:161-165
+    filtered_output = filtered_logit(src, output).reshape(-1, cc.vocab_size)
+    return F.cross_entropy(filtered_output, trg.reshape(-1))
+
+
+def train_step(model, optimizer, src, trg, meta, autocast_dtype=None):
+    """One iteration of the reference's hot loop (train.py:160-169): returns the loss tensor (no .item())."""
+    with torch.autocast("cuda", dtype=autocast_dtype, enabled=autocast_dtype is not None):
+        output = model(src, meta)
+    loss = loss_fn(src, trg, output)
+    optimizer.zero_grad(set_to_none=False)
+    loss.backward()
+    optimizer.step()
+    return loss
+
+
+class Trainer:
+    """The reference's training step as ONE CUDA graph per rank.
+
+    `train_parallel.py:143-185` wraps the model in DDP (gradient all-reduce(mean) over NCCL, overlapped with
+    backward) and launches every kernel from python.  At the reference's batch (2 x 2048 tokens per GPU) the
+    step is a few milliseconds of GPU work, so launch latency and the exposed all-reduce dominate.  Here
+    the whole step — H2D-staged batch -> forward -> loss -> backward -> all-reduce of the flat gradient
+    buffer -> Adam — is captured once and replayed; the gradients of all parameters live in one flat buffer
+    (bucket views) so the data-parallel exchange is `n_buckets` NCCL all-reduces issued inside the graph
+    on a side stream as soon as each bucket's last gradient is produced.
+    """
+
+    def __init__(self, model, lr=None, autocast_dtype=torch.bfloat16, world_size=1, process_group=None,
+                 batch_size=None, block_len=None, use_graph=True, bucket_mb=64):
+        self.model = model
+        self.device = next(model.parameters()).device
+        self.autocast_dtype = autocast_dtype
+        self.world_size = world_size
+        self.pg = process_group
+        B = cc.config.values.batch_size if batch_size is None else batch_size
+        T = cc.config.values.block_len if block_len is None else block_len
+        self.src = torch.zeros(B, T, dtype=torch.long, device=self.device)
+        self.trg = torch.zeros(B, T, dtype=torch.long, device=self.device)
+        self.meta = torch.zeros(B, cc.N_META, dtype=torch.long, device=self.device)
+        self.loss = torch.zeros((), device=self.device)
+        self._flatten_grads(bucket_mb)
+        lr = cc.config.values.learning_rate if lr is None else lr
+        self.optimizer = torch.optim.Adam(model.parameters(), lr=lr, capturable=use_graph, fused=True)  # train.py:146
+        self.use_graph = use_graph
+        self.graph = None
+
+    # one flat fp32 gradient buffer; every p.grad is a view into it
+    def _flatten_grads(self, bucket_mb):
+        params = [p for p in self.model.parameters() if p.requires_grad]
+        total = sum(p.numel() for p in params)
+        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=self.device)
+        off = 0
+        for p in params:
+            p.grad = self.flat_grad[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        per = max(1, int(bucket_mb * (1 << 20) // 4))
+        self.buckets = [self.flat_grad[i:i + per] for i in range(0, total, per)]
+
+    def _allreduce(self):
+        if self.world_size <= 1:
+            return
+        import torch.distributed as dist
+        for b in self.buckets:
+            dist.all_reduce(b, op=dist.ReduceOp.AVG, group=self.pg)
+
+    def _step_body(self):
+        with torch.autocast("cuda", dtype=self.autocast_dtype, enabled=self.autocast_dtype is not None):
+            output = self.model(self.src, self.meta)
+        loss = loss_fn(self.src, self.trg, output)
+        self.flat_grad.zero_()
+        loss.backward()
+        self._allreduce()
+        self.optimizer.step()
+        self.loss.copy_(loss.detach())
+
+    def capture(self, warmup=3):
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                self._step_body()
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        torch.cuda.synchronize(self.device)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._step_body()
+
+    def step(self, src, trg, meta):
+        """src/trg/meta: host (pinned) or device tensors of the configured shape.  Returns the device-side
+        loss scalar (read it with .item() only when you need it: train.py:171 syncs every step)."""
+        self.src.copy_(src, non_blocking=True)
+        self.trg.copy_(trg, non_blocking=True)
+        self.meta.copy_(meta, non_blocking=True)
+        if self.use_graph:
+            if self.graph is None:
+                self.capture()
+            self.graph.replay()
+        else:
+            self._step_body()
+        return self.loss

@@ -1,0 +1,259 @@
+/*
+ * mamba_b200.h — C-ABI of the B200-native (sm_100a) Mamba hot path.
+ *
+ * The reference (thorGabe123/Deep-Learning-Based-Sequence-Models-for-Music-Generation) has
+ * no FFI of its own: its hot path is Python (`nn.Module` duck typing).  Every entry point
+ * below therefore cites the *Python* statement(s) of the reference it replaces.  Paths are
+ * relative to the reference root; `simple_mamba.pyc @Lnnn` means original source line nnn of
+ * models/mamba/__pycache__/simple_mamba.cpython-311.pyc (the pure-PyTorch Mamba-1 whose
+ * source file was deleted upstream; transcription in SURVEY.md Appendix A).
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no torch types.  All pointers are DEVICE pointers unless
+ *    the name ends in `_host`.
+ *  - the caller owns and allocates every input, output and workspace buffer; the library
+ *    keeps no global state, never allocates, never synchronises, and enqueues all work on the
+ *    `stream` argument (a `cudaStream_t` passed as `void*`).
+ *  - activations are row-major `[batch, seqlen, channels]` with the channel axis contiguous;
+ *    `*_bs` / `*_ls` are the batch and sequence strides IN ELEMENTS, so the split views the
+ *    reference takes of `in_proj(x)` and `x_proj(x)` are consumed without a copy.
+ *  - `dtype` selects the activation I/O element type (MAMBA_F32 or MAMBA_BF16).  Parameters
+ *    A, D, delta_bias, their gradients, the SSM state and all accumulation are always fp32.
+ *  - every function returns MAMBA_OK (0) or a negative MAMBA_E* code; `mamba_last_error()`
+ *    returns a thread-local human-readable message for the last failure on this thread.
+ */
+#ifndef MAMBA_B200_H_
+#define MAMBA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MAMBA_ABI_VERSION 1
+
+enum { MAMBA_F32 = 0, MAMBA_BF16 = 1 };
+
+enum {
+  MAMBA_OK = 0,
+  MAMBA_EINVAL = -1,   /* bad shape / null pointer / bad struct_size            */
+  MAMBA_EDTYPE = -2,   /* unsupported dtype                                     */
+  MAMBA_EALIGN = -3,   /* pointer or stride breaks the documented alignment     */
+  MAMBA_ELAUNCH = -4,  /* CUDA launch failure (cudaPeekAtLastError != success)  */
+  MAMBA_ESIZE = -5     /* workspace too small / dimension above supported limit */
+};
+
+enum {
+  MAMBA_FLAG_HAS_Z = 1,          /* out = y * silu(z)             (simple_mamba.pyc @L241)  */
+  MAMBA_FLAG_DELTA_SOFTPLUS = 2, /* delta = softplus(delta_raw)   (simple_mamba.pyc @L276)  */
+  MAMBA_FLAG_HAS_DELTA_BIAS = 4, /* delta_raw += delta_bias[d]    (dt_proj bias, @L276)     */
+  MAMBA_FLAG_HAS_D = 8           /* y += u * D                    (simple_mamba.pyc @L331)  */
+};
+
+/* ------------------------------------------------------------------------------------------
+ * Selective scan (forward).  Replaces MambaBlock.selective_scan (simple_mamba.pyc @L310-333)
+ * fused with softplus (@L276), the D skip (@L331) and the z gate (@L241):
+ *     delta = softplus(delta_raw + delta_bias)                       (threshold 20, as F.softplus)
+ *     h_t   = exp(delta_t * A) * h_{t-1} + delta_t * B_t * u_t        (h_{-1} = 0, per (b, d, n))
+ *     y_t   = <h_t, C_t> + D * u_t
+ *     out_t = y_t * silu(z_t)
+ * The [B, L, D, N] tensors deltaA / deltaB_u of the reference are never materialised.
+ * When `ckpt` is non-null the state at the start of every `chunk`-timestep block is written to
+ * it (fp32, layout [batch, nchunks, dstate, dim], nchunks = ceil(seqlen/chunk); slot 0 is not
+ * written) for use by mamba_scan_bwd.  When `h_last` is non-null the final state h_{L-1} is
+ * written to it ([batch, dim, dstate] fp32 — the decode step's `ssm_state` layout).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct MambaScanFwdArgs {
+  int32_t struct_size; /* = sizeof(MambaScanFwdArgs) */
+  int32_t dtype;
+  int32_t batch, seqlen, dim, dstate;
+  int32_t chunk; /* checkpoint interval in timesteps: 8, 16 or 32 (ignored if ckpt == NULL) */
+  int32_t flags;
+  int32_t variant; /* 0 = auto; otherwise states per thread (4, 8 or 16) — tuning knob */
+  int32_t reserved;
+  const void* u;     int64_t u_bs, u_ls;         /* [B, L, D]                 */
+  const void* delta; int64_t delta_bs, delta_ls; /* [B, L, D] raw dt_proj out */
+  const float* A;                                /* [D, N]  (= -exp(A_log))   */
+  const void* B;     int64_t B_bs, B_ls;         /* [B, L, N]                 */
+  const void* C;     int64_t C_bs, C_ls;         /* [B, L, N]                 */
+  const float* D;                                /* [D] or NULL               */
+  const void* z;     int64_t z_bs, z_ls;         /* [B, L, D] or NULL         */
+  const float* delta_bias;                       /* [D] or NULL               */
+  void* out;         int64_t out_bs, out_ls;     /* [B, L, D]                 */
+  float* ckpt;                                   /* see above, or NULL        */
+  float* h_last;                                 /* [B, D, N] or NULL         */
+  const float* h_init;                           /* [B, D, N] or NULL (zeros) */
+} MambaScanFwdArgs;
+
+int mamba_scan_fwd(const MambaScanFwdArgs* args, void* stream);
+
+/* Number of floats in the `ckpt` buffer for the given problem. */
+size_t mamba_scan_ckpt_elems(int batch, int seqlen, int dim, int dstate, int chunk);
+
+/* ------------------------------------------------------------------------------------------
+ * Selective scan (backward).  Replaces what torch autograd derives from the Python loop of
+ * simple_mamba.pyc @L310-333 (+ softplus/D/z as above).  The forward is recomputed inside each
+ * `chunk` from the checkpoints written by mamba_scan_fwd; nothing of size B*L*D*N touches HBM.
+ * Gradients du/ddelta/dz/dB/dC have the activation dtype; ddelta is w.r.t. delta_raw (softplus
+ * derivative applied).  dA [D, N], dD [D], ddelta_bias [D] are fp32 and are OVERWRITTEN.
+ * `workspace` must hold mamba_scan_bwd_workspace_bytes(...) bytes (any contents).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct MambaScanBwdArgs {
+  int32_t struct_size;
+  int32_t dtype;
+  int32_t batch, seqlen, dim, dstate;
+  int32_t chunk;
+  int32_t flags;
+  int32_t variant;
+  int32_t reserved;
+  const void* u;     int64_t u_bs, u_ls;
+  const void* delta; int64_t delta_bs, delta_ls;
+  const float* A;
+  const void* B;     int64_t B_bs, B_ls;
+  const void* C;     int64_t C_bs, C_ls;
+  const float* D;
+  const void* z;     int64_t z_bs, z_ls;
+  const float* delta_bias;
+  const void* dout;  int64_t dout_bs, dout_ls;
+  const float* ckpt;
+  void* du;          int64_t du_bs, du_ls;
+  void* ddelta;      int64_t ddelta_bs, ddelta_ls;
+  void* dz;          int64_t dz_bs, dz_ls;         /* NULL iff !HAS_Z */
+  void* dB;          int64_t dB_bs, dB_ls;
+  void* dC;          int64_t dC_bs, dC_ls;
+  float* dA;
+  float* dD;          /* NULL iff !HAS_D          */
+  float* ddelta_bias; /* NULL iff !HAS_DELTA_BIAS */
+  void* workspace;
+  size_t workspace_bytes;
+} MambaScanBwdArgs;
+
+int mamba_scan_bwd(const MambaScanBwdArgs* args, void* stream);
+size_t mamba_scan_bwd_workspace_bytes(int batch, int seqlen, int dim, int dstate);
+
+/* ------------------------------------------------------------------------------------------
+ * Causal depthwise conv1d + SiLU.  Replaces
+ *     x = rearrange(x,'b l d -> b d l'); x = self.conv1d(x)[:, :, :l]; rearrange back; F.silu(x)
+ * (simple_mamba.pyc @L233-237; nn.Conv1d(groups=d_inner, kernel_size=d_conv, padding=d_conv-1)
+ * built at @L193-199):   out[b,t,d] = silu(bias[d] + sum_k w[d,k] * x[b, t-(K-1)+k, d]).
+ * weight is [D, K] contiguous fp32 (the reference's [D,1,K] Conv1d weight viewed 2-D), bias [D]
+ * fp32 or NULL, 2 <= K <= 4.  No transposes: x stays [B, L, D].
+ * `final_state` (optional, [B, D, K] activation dtype) receives the last K inputs of each
+ * channel (zero-padded on the left) — the decode step's `conv_state`.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct MambaConvArgs {
+  int32_t struct_size;
+  int32_t dtype;
+  int32_t batch, seqlen, dim, width;
+  const void* x;   int64_t x_bs, x_ls;
+  const float* weight;
+  const float* bias;
+  void* out;       int64_t out_bs, out_ls;
+  void* final_state;
+  /* backward only */
+  const void* dout; int64_t dout_bs, dout_ls;
+  void* dx;         int64_t dx_bs, dx_ls;
+  float* dweight;  /* [D, K] fp32, overwritten */
+  float* dbias;    /* [D]    fp32, overwritten (NULL iff bias == NULL) */
+  void* workspace;
+  size_t workspace_bytes;
+} MambaConvArgs;
+
+int mamba_conv1d_silu_fwd(const MambaConvArgs* args, void* stream);
+int mamba_conv1d_silu_bwd(const MambaConvArgs* args, void* stream);
+size_t mamba_conv1d_bwd_workspace_bytes(int batch, int seqlen, int dim, int width);
+
+/* ------------------------------------------------------------------------------------------
+ * Single-token recurrent step (decode).  The reference has no such step (its generate() re-runs
+ * the whole model on a sliding window, scripts/generate.py:26-31); this is the recurrence of
+ * simple_mamba.pyc @L233-241 and @L310-333 evaluated for one new position with carried state.
+ *
+ * mamba_conv_step:  conv_state[b,d,:] is shifted left by one, x_t appended, and
+ *     xc[b,d] = silu(bias[d] + sum_k w[d,k] * conv_state[b,d,k])
+ * mamba_ssm_step:   delta = softplus(dt_w[d,:] . dt_in[b,:] + dt_b[d])     (dt_proj fused, @L276)
+ *     h[b,d,:] = exp(delta*A[d,:]) * h[b,d,:] + delta * Bv[b,:] * xc[b,d]
+ *     y[b,d]   = (<h[b,d,:], Cv[b,:]> + D[d]*xc[b,d]) * silu(z[b,d])
+ * conv_state is [B, D, K] and ssm_state [B, D, N] fp32, both updated in place.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct MambaStepArgs {
+  int32_t struct_size;
+  int32_t dtype;
+  int32_t batch, dim, dstate, width, dt_rank;
+  int32_t flags;
+  /* conv step */
+  const void* x;  int64_t x_bs;           /* [B, D] new input column (in_proj x half) */
+  void* conv_state;                       /* [B, D, K] activation dtype               */
+  const float* conv_weight;               /* [D, K] */
+  const float* conv_bias;                 /* [D] or NULL */
+  void* xc;       int64_t xc_bs;          /* [B, D] out of conv step / in of ssm step */
+  /* ssm step */
+  const void* dt_in; int64_t dt_in_bs;    /* [B, R] low-rank delta (x_proj split)     */
+  const void* Bv;    int64_t Bv_bs;       /* [B, N] */
+  const void* Cv;    int64_t Cv_bs;       /* [B, N] */
+  const float* dt_weight;                 /* [D, R] fp32 */
+  const float* dt_bias;                   /* [D]    fp32 or NULL */
+  const float* A;                         /* [D, N] */
+  const float* D;                         /* [D] or NULL */
+  const void* z;     int64_t z_bs;        /* [B, D] or NULL */
+  float* ssm_state;                       /* [B, D, N] fp32 */
+  void* y;           int64_t y_bs;        /* [B, D] */
+} MambaStepArgs;
+
+int mamba_conv_step(const MambaStepArgs* args, void* stream);
+int mamba_ssm_step(const MambaStepArgs* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * RMSNorm with fused residual add.  Replaces RMSNorm.forward (simple_mamba.pyc @L346) and the
+ * `+ x` of ResidualBlock.forward (@L179):
+ *     r = x + residual   (either operand may be NULL, not both; the sum is rounded to resid_dtype
+ *                         when residual != NULL so that what is normalised is what is stored)
+ *     y = r * rsqrt(mean(r^2) + eps) * weight
+ * Two element types: `dtype` for the mixer-side activations (x, y, dy, dx) and `resid_dtype` for the
+ * residual stream (residual, resid_out, dresid_in, dresid_out) — the stream can stay fp32 while the
+ * mixer runs in bf16.  Supported (dtype, resid_dtype): (F32,F32), (BF16,F32), (BF16,BF16).
+ * Backward: `residual` must point to the tensor that was normalised (resid_out of the forward, or x
+ * itself — then pass resid_dtype = dtype); with g = dy*w, rh = r*rstd:
+ *     dr = rstd * (g - rh * mean(g*rh)) + dresid_in;   dweight[c] = sum_rows dy*rh   (overwritten)
+ * dr is written to dx (dtype) and/or dresid_out (resid_dtype); at least one must be non-NULL.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct MambaNormArgs {
+  int32_t struct_size;
+  int32_t dtype;
+  int32_t resid_dtype;
+  int32_t dim;
+  int64_t rows;
+  float eps;
+  int32_t reserved;
+  const void* x;        /* [rows, dim] dtype, contiguous, or NULL      */
+  const void* residual; /* [rows, dim] resid_dtype or NULL             */
+  const float* weight;  /* [dim] fp32                                  */
+  void* y;              /* [rows, dim] dtype                           */
+  void* resid_out;      /* [rows, dim] resid_dtype or NULL             */
+  float* rstd;          /* [rows] fp32 or NULL (saved for backward)    */
+  /* backward only */
+  const void* dy;        /* [rows, dim] dtype                          */
+  const void* dresid_in; /* [rows, dim] resid_dtype or NULL: gradient arriving on resid_out */
+  void* dx;              /* [rows, dim] dtype or NULL                  */
+  void* dresid_out;      /* [rows, dim] resid_dtype or NULL            */
+  float* dweight;        /* [dim] fp32 overwritten                     */
+  void* workspace;
+  size_t workspace_bytes;
+} MambaNormArgs;
+
+int mamba_rmsnorm_fwd(const MambaNormArgs* args, void* stream);
+int mamba_rmsnorm_bwd(const MambaNormArgs* args, void* stream);
+size_t mamba_rmsnorm_bwd_workspace_bytes(int64_t rows, int dim);
+
+/* ------------------------------------------------------------------------------------------ */
+int mamba_abi_version(void);
+const char* mamba_last_error(void);
+/* Number of kernels this library has launched from the calling process (monotonic counter;
+ * bench.py reports the difference across the timed region as "gpu_launches"). */
+uint64_t mamba_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAMBA_B200_H_ */

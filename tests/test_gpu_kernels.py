@@ -1,0 +1,388 @@
+"""GPU parity tests: every CUDA kernel (through the C-ABI, via mamba_b200.ops) against the CPU oracle.
+
+Tolerances (BASELINE.json north_star): fp32 rtol 1e-4 on outputs and gradients, with an absolute floor of
+1e-5 * max|ref| (a gradient that is a sum of many signed terms cannot be held to a pure relative bound at
+its zero crossings).  bf16 I/O: rtol 2e-2 / floor 2e-2 * max|ref| against the fp32 oracle evaluated on the
+same bf16-rounded inputs (one bf16 rounding of the output is 2^-9 = 0.2 %; the floor covers cancellation).
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import simple_mamba as om
+from util import assert_close, scan_inputs
+
+pytestmark = pytest.mark.gpu
+
+RTOL32 = 1e-4
+RTOL16, FLOOR16 = 2e-2, 2e-2
+
+
+def _oracle_scan(t, has_z=True, has_D=True, has_bias=True, softplus=True, last_state=False):
+    """Oracle evaluation of the fused op: softplus(dt+bias) -> selective_scan (+D*u) -> * silu(z)."""
+    d = t["delta_raw"].float()
+    if has_bias:
+        d = d + t["bias"]
+    if softplus:
+        d = F.softplus(d)
+    D = t["D"] if has_D else torch.zeros_like(t["D"])
+    y, h = om.selective_scan(t["u"].float(), d, t["A"], t["B"].float(), t["C"].float(), D, return_last_state=True)
+    if has_z:
+        y = y * F.silu(t["z"].float())
+    return (y, h) if last_state else y
+
+
+def _leafs(t, device, names=("u", "delta_raw", "A", "B", "C", "D", "z", "bias")):
+    return {k: t[k].detach().clone().to(device).requires_grad_(True) for k in names}
+
+
+SHAPES = [  # (B, L, D, N)
+    (1, 1, 32, 16),       # single timestep
+    (2, 7, 32, 16),       # shorter than any chunk
+    (2, 33, 64, 16),      # one step past a stage boundary
+    (1, 100, 96, 64),     # repo d_state, L not a multiple of the chunk
+    (2, 257, 40, 8),      # D not a multiple of 32 (ragged channel tile), N = 8
+    (1, 64, 32, 5),       # odd d_state
+    (1, 130, 36, 48),     # D % 4 == 0 but % 32 != 0, N = 48
+]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_scan_forward_fp32(shape):
+    from mamba_b200 import ops
+    B, L, D, N = shape
+    t = scan_inputs(B, L, D, N, seed=1)
+    ref, href = _oracle_scan(t, last_state=True)
+    g = {k: v.cuda() for k, v in t.items()}
+    out = ops.selective_scan_fn(g["u"], g["delta_raw"], g["A"], g["B"], g["C"], g["D"], z=g["z"],
+                                delta_bias=g["bias"], delta_softplus=True)
+    assert_close(out, ref, RTOL32, what=f"scan fwd {shape}")
+    out2, h = ops.selective_scan_prefill(g["u"], g["delta_raw"], g["A"], g["B"], g["C"], g["D"], z=g["z"],
+                                         delta_bias=g["bias"], delta_softplus=True)
+    assert torch.equal(out, out2)
+    assert_close(h, href, RTOL32, what=f"scan last state {shape}")
+
+
+@pytest.mark.parametrize("flags", [(False, False, False, False), (True, False, True, False), (False, True, False, True)])
+def test_scan_forward_flag_combinations(flags):
+    from mamba_b200 import ops
+    has_z, has_D, has_bias, softplus = flags
+    t = scan_inputs(2, 50, 64, 16, seed=2)
+    if not softplus:
+        t["delta_raw"] = F.softplus(t["delta_raw"])  # a positive step either way
+    ref = _oracle_scan(t, has_z, has_D, has_bias, softplus)
+    g = {k: v.cuda() for k, v in t.items()}
+    out = ops.selective_scan_fn(g["u"], g["delta_raw"], g["A"], g["B"], g["C"], g["D"] if has_D else None,
+                                z=g["z"] if has_z else None, delta_bias=g["bias"] if has_bias else None,
+                                delta_softplus=softplus)
+    assert_close(out, ref, RTOL32, what=f"scan fwd flags {flags}")
+
+
+def test_scan_forward_strided_views_and_softplus_threshold():
+    """The module passes split() views of in_proj / x_proj outputs; delta_raw above 20 takes the identity branch."""
+    from mamba_b200 import ops
+    B, L, D, N, R = 2, 40, 64, 16, 4
+    g = torch.Generator().manual_seed(5)
+    xz = torch.randn(B, L, 2 * D, generator=g)
+    xdbl = torch.randn(B, L, R + 2 * N, generator=g)
+    dt = torch.randn(B, L, D, generator=g) - 4
+    dt[0, 3, :8] = 25.0
+    dt[1, 0, 5] = 20.0
+    A = -torch.rand(D, N, generator=g) - 0.5
+    Dv = torch.randn(D, generator=g)
+    u, z = xz.split([D, D], dim=-1)
+    _, Bm, Cm = xdbl.split([R, N, N], dim=-1)
+    ref = _oracle_scan(dict(u=u, z=z, delta_raw=dt, A=A, B=Bm, C=Cm, D=Dv, bias=None), has_bias=False)
+    xzg, xdg = xz.cuda(), xdbl.cuda()
+    ug, zg = xzg.split([D, D], dim=-1)
+    _, Bg, Cg = xdg.split([R, N, N], dim=-1)
+    out = ops.selective_scan_fn(ug, dt.cuda(), A.cuda(), Bg, Cg, Dv.cuda(), z=zg, delta_softplus=True)
+    assert_close(out, ref, RTOL32, what="scan fwd strided")
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("chunk", [8, 16])
+def test_scan_backward_fp32(shape, chunk):
+    from mamba_b200 import ops
+    B, L, D, N = shape
+    t = scan_inputs(B, L, D, N, seed=3)
+    gen = torch.Generator().manual_seed(9)
+    dout = torch.randn(B, L, D, generator=gen)
+    c = _leafs(t, "cpu")
+    ref = _oracle_scan(c)
+    ref.backward(dout)
+    g = _leafs(t, "cuda")
+    out = ops.selective_scan_fn(g["u"], g["delta_raw"], g["A"], g["B"], g["C"], g["D"], z=g["z"],
+                                delta_bias=g["bias"], delta_softplus=True, chunk=chunk)
+    out.backward(dout.cuda())
+    assert_close(out, ref, RTOL32, what=f"scan fwd (grad run) {shape}")
+    for k in c:
+        assert_close(g[k].grad, c[k].grad, RTOL32, what=f"scan bwd d{k} {shape} chunk {chunk}")
+
+
+def test_scan_backward_without_optional_inputs():
+    from mamba_b200 import ops
+    t = scan_inputs(2, 37, 64, 16, seed=4)
+    t["delta_raw"] = F.softplus(t["delta_raw"])
+    names = ("u", "delta_raw", "A", "B", "C")
+    c = _leafs(t, "cpu", names)
+    ref = om.selective_scan(c["u"], c["delta_raw"], c["A"], c["B"], c["C"], torch.zeros(64))
+    dout = torch.randn(2, 37, 64, generator=torch.Generator().manual_seed(1))
+    ref.backward(dout)
+    g = _leafs(t, "cuda", names)
+    out = ops.selective_scan_fn(g["u"], g["delta_raw"], g["A"], g["B"], g["C"])
+    out.backward(dout.cuda())
+    assert_close(out, ref, RTOL32, what="scan fwd plain")
+    for k in names:
+        assert_close(g[k].grad, c[k].grad, RTOL32, what=f"scan bwd plain d{k}")
+
+
+def test_scan_bf16_io():
+    from mamba_b200 import ops
+    B, L, D, N = 2, 150, 64, 16
+    t = scan_inputs(B, L, D, N, seed=6, dtype=torch.bfloat16)
+    dout = torch.randn(B, L, D, generator=torch.Generator().manual_seed(2)).bfloat16()
+    c = _leafs(t, "cpu")
+    ref = _oracle_scan(c)
+    ref.backward(dout.float())
+    g = _leafs(t, "cuda")
+    out = ops.selective_scan_fn(g["u"], g["delta_raw"], g["A"], g["B"], g["C"], g["D"], z=g["z"],
+                                delta_bias=g["bias"], delta_softplus=True)
+    assert out.dtype == torch.bfloat16
+    out.backward(dout.cuda())
+    assert_close(out, ref, RTOL16, FLOOR16, what="scan fwd bf16")
+    for k in c:
+        assert g[k].grad.dtype == g[k].dtype
+        assert_close(g[k].grad, c[k].grad, RTOL16, FLOOR16, what=f"scan bwd bf16 d{k}")
+
+
+def test_scan_state_carry_composes_at_full_size():
+    """Size-independent property at BASELINE's long-context shape (L=8192, N=16, D=2048): scanning the whole
+    sequence equals scanning two halves with the state carried (h_init), and equals the oracle on a slice."""
+    from mamba_b200 import ops
+    B, L, D, N = 1, 8192, 2048, 16
+    t = scan_inputs(B, L, D, N, seed=7)
+    g = {k: v.cuda() for k, v in t.items()}
+    kw = dict(delta_softplus=True)
+    full, h_full = ops.selective_scan_prefill(g["u"], g["delta_raw"], g["A"], g["B"], g["C"], g["D"], z=g["z"],
+                                              delta_bias=g["bias"], **kw)
+    cut = 3001
+    a, h_a = ops.selective_scan_prefill(g["u"][:, :cut], g["delta_raw"][:, :cut], g["A"], g["B"][:, :cut],
+                                        g["C"][:, :cut], g["D"], z=g["z"][:, :cut], delta_bias=g["bias"], **kw)
+    b, h_b = ops.selective_scan_prefill(g["u"][:, cut:], g["delta_raw"][:, cut:], g["A"], g["B"][:, cut:],
+                                        g["C"][:, cut:], g["D"], z=g["z"][:, cut:], delta_bias=g["bias"],
+                                        h_init=h_a, **kw)
+    assert torch.equal(torch.cat((a, b), dim=1), full)       # same arithmetic order => bit-equal
+    assert torch.equal(h_b, h_full)
+    sl = slice(0, 96)                                          # oracle on a channel slice, first 300 steps
+    ts = {k: (v[:, :300, sl] if k in ("u", "z", "delta_raw") else v) for k, v in t.items()}
+    ts["A"], ts["D"], ts["bias"] = t["A"][sl], t["D"][sl], t["bias"][sl]
+    ts["B"], ts["C"] = t["B"][:, :300], t["C"][:, :300]
+    assert_close(full[:, :300, sl], _oracle_scan(ts), RTOL32, what="full-size scan vs oracle slice")
+
+
+def test_scan_linearity_in_u_at_repo_shape():
+    """Property at the repo's training shape (B=2, L=2054, D=2048, N=64): without the gate the scan is linear
+    in u:  scan(u1 + 2*u2) = scan(u1) + 2*scan(u2)."""
+    from mamba_b200 import ops
+    B, L, D, N = 2, 2054, 2048, 64
+    t = scan_inputs(B, L, D, N, seed=8)
+    g = {k: v.cuda() for k, v in t.items()}
+    u2 = torch.randn(B, L, D, generator=torch.Generator().manual_seed(11)).cuda()
+
+    def run(u):
+        return ops.selective_scan_fn(u, g["delta_raw"], g["A"], g["B"], g["C"], g["D"], delta_bias=g["bias"],
+                                     delta_softplus=True)
+
+    lhs = run(g["u"] + 2 * u2)
+    rhs = run(g["u"]) + 2 * run(u2)
+    assert_close(lhs, rhs, 1e-4, 1e-5, what="scan linearity")
+
+
+# ---------------------------------------------------------------------------------------------------
+# causal depthwise conv1d + SiLU
+# ---------------------------------------------------------------------------------------------------
+def _oracle_conv(x, w, b):
+    """simple_mamba @L233-237 with nn.Conv1d(groups=D, padding=K-1) built at @L193-199."""
+    L = x.shape[1]
+    y = F.conv1d(x.transpose(1, 2), w, b, padding=w.shape[-1] - 1, groups=w.shape[0])[:, :, :L]
+    return F.silu(y.transpose(1, 2))
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 32, 4), (2, 3, 64, 4), (2, 100, 96, 4), (1, 257, 40, 4), (2, 65, 33, 3),
+                                   (1, 40, 64, 2), (2, 2054, 128, 4)])
+def test_conv1d_silu_fwd_bwd_fp32(shape):
+    from mamba_b200 import ops
+    B, L, D, K = shape
+    gen = torch.Generator().manual_seed(L)
+    x = torch.randn(B, L, D, generator=gen)
+    w = torch.randn(D, 1, K, generator=gen) * 0.5
+    b = torch.randn(D, generator=gen) * 0.1
+    dout = torch.randn(B, L, D, generator=gen)
+    xc, wc, bc = (v.clone().requires_grad_(True) for v in (x, w, b))
+    ref = _oracle_conv(xc, wc, bc)
+    ref.backward(dout)
+    xg, wg, bg = (v.clone().cuda().requires_grad_(True) for v in (x, w, b))
+    out = ops.causal_conv1d_silu_fn(xg, wg, bg)
+    out.backward(dout.cuda())
+    assert_close(out, ref, RTOL32, what=f"conv fwd {shape}")
+    assert_close(xg.grad, xc.grad, RTOL32, what=f"conv dx {shape}")
+    assert_close(wg.grad, wc.grad, RTOL32, what=f"conv dw {shape}")
+    assert_close(bg.grad, bc.grad, RTOL32, what=f"conv db {shape}")
+
+
+def test_conv1d_strided_input_no_bias_and_final_state():
+    from mamba_b200 import ops
+    B, L, D, K = 2, 50, 64, 4
+    gen = torch.Generator().manual_seed(0)
+    xz = torch.randn(B, L, 2 * D, generator=gen)
+    w = torch.randn(D, 1, K, generator=gen)
+    ref = _oracle_conv(xz[..., :D], w, None)
+    xg = xz.cuda()[..., :D]
+    out = ops.causal_conv1d_silu_fn(xg, w.cuda(), None)
+    assert_close(out, ref, RTOL32, what="conv strided")
+    out2, state = ops.causal_conv1d_silu_prefill(xg, w.cuda(), None)
+    assert torch.equal(out, out2)
+    assert torch.equal(state.cpu(), xz[:, -K:, :D].transpose(1, 2))
+    # shorter than the kernel: left zero padding of the state
+    _, st2 = ops.causal_conv1d_silu_prefill(xg[:, :2], w.cuda(), None)
+    exp = torch.zeros(B, D, K)
+    exp[:, :, 2:] = xz[:, :2, :D].transpose(1, 2)
+    assert torch.equal(st2.cpu(), exp)
+
+
+def test_conv1d_bf16():
+    from mamba_b200 import ops
+    B, L, D, K = 2, 130, 64, 4
+    gen = torch.Generator().manual_seed(1)
+    x = torch.randn(B, L, D, generator=gen).bfloat16()
+    w = torch.randn(D, 1, K, generator=gen) * 0.5
+    b = torch.randn(D, generator=gen) * 0.1
+    dout = torch.randn(B, L, D, generator=gen).bfloat16()
+    xc, wc, bc = x.float().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref = _oracle_conv(xc, wc, bc)
+    ref.backward(dout.float())
+    xg, wg, bg = x.cuda().requires_grad_(True), w.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
+    out = ops.causal_conv1d_silu_fn(xg, wg, bg)
+    out.backward(dout.cuda())
+    assert out.dtype == torch.bfloat16 and xg.grad.dtype == torch.bfloat16 and wg.grad.dtype == torch.float32
+    assert_close(out, ref, RTOL16, FLOOR16, what="conv bf16 fwd")
+    assert_close(xg.grad, xc.grad, RTOL16, FLOOR16, what="conv bf16 dx")
+    assert_close(wg.grad, wc.grad, RTOL16, FLOOR16, what="conv bf16 dw")
+    assert_close(bg.grad, bc.grad, RTOL16, FLOOR16, what="conv bf16 db")
+
+
+# ---------------------------------------------------------------------------------------------------
+# RMSNorm (+ residual)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("rows_dim", [((2, 5), 32), ((3, 7), 100), ((2, 2054), 1024), ((1, 9), 2048), ((4,), 36)])
+def test_rmsnorm_plain_fp32(rows_dim):
+    from mamba_b200 import ops
+    lead, dim = rows_dim
+    gen = torch.Generator().manual_seed(dim)
+    x = torch.randn(*lead, dim, generator=gen)
+    w = 1 + 0.1 * torch.randn(dim, generator=gen)
+    dy = torch.randn(*lead, dim, generator=gen)
+    norm = om.RMSNorm(dim)
+    with torch.no_grad():
+        norm.weight.copy_(w)
+    xc = x.clone().requires_grad_(True)
+    ref = norm(xc)
+    ref.backward(dy)
+    xg, wg = x.cuda().requires_grad_(True), w.cuda().requires_grad_(True)
+    out, stream = ops.rmsnorm_fn(xg, wg)
+    assert stream is xg
+    out.backward(dy.cuda())
+    assert_close(out, ref, RTOL32, what=f"rmsnorm fwd {rows_dim}")
+    assert_close(xg.grad, xc.grad, RTOL32, what=f"rmsnorm dx {rows_dim}")
+    assert_close(wg.grad, norm.weight.grad, RTOL32, what=f"rmsnorm dw {rows_dim}")
+
+
+@pytest.mark.parametrize("dtypes", [(torch.float32, torch.float32), (torch.bfloat16, torch.float32),
+                                    (torch.bfloat16, torch.bfloat16)])
+def test_rmsnorm_fused_residual(dtypes):
+    """y = norm(x + residual), stream = x + residual, gradients reach both operands (ResidualBlock @L179)."""
+    from mamba_b200 import ops
+    T, TR = dtypes
+    gen = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 11, 128, generator=gen).to(T)
+    r = torch.randn(2, 11, 128, generator=gen).to(TR)
+    w = 1 + 0.1 * torch.randn(128, generator=gen)
+    dy = torch.randn(2, 11, 128, generator=gen).to(T)
+    ds = torch.randn(2, 11, 128, generator=gen).to(TR)
+    xc, rc, wc = x.float().requires_grad_(True), r.float().requires_grad_(True), w.clone().requires_grad_(True)
+    s_ref = (xc + rc).to(TR).float() if TR != torch.float32 else xc + rc
+    s_ref = xc + rc
+    y_ref = s_ref * torch.rsqrt(s_ref.pow(2).mean(-1, keepdim=True) + 1e-5) * wc
+    (y_ref * dy.float()).sum().backward(retain_graph=True)
+    (s_ref * ds.float()).sum().backward()
+    xg, rg, wg = x.cuda().requires_grad_(True), r.cuda().requires_grad_(True), w.cuda().requires_grad_(True)
+    y, s = ops.rmsnorm_fn(xg, wg, rg, 1e-5, T)
+    assert y.dtype == T and s.dtype == TR
+    torch.autograd.backward([y, s], [dy.cuda(), ds.cuda()])
+    lo = T == torch.float32
+    rt, fl = (RTOL32, 1e-5) if lo else (RTOL16, FLOOR16)
+    assert_close(y, y_ref, rt, fl, what=f"rmsnorm fused y {dtypes}")
+    assert_close(s, s_ref, RTOL32 if TR == torch.float32 else RTOL16, 1e-5 if TR == torch.float32 else FLOOR16,
+                 what=f"rmsnorm fused stream {dtypes}")
+    assert xg.grad.dtype == T and rg.grad.dtype == TR
+    assert_close(xg.grad, xc.grad, rt, fl, what=f"rmsnorm fused dx {dtypes}")
+    assert_close(rg.grad, rc.grad, rt, fl, what=f"rmsnorm fused dres {dtypes}")
+    assert_close(wg.grad, wc.grad, rt, fl, what=f"rmsnorm fused dw {dtypes}")
+
+
+def test_rmsnorm_residual_only_first_layer_form():
+    """First layer: no mixer output yet, the stream is the embedding itself; y may be bf16 over an fp32 stream."""
+    from mamba_b200 import ops
+    gen = torch.Generator().manual_seed(4)
+    r = torch.randn(3, 5, 64, generator=gen)
+    w = 1 + 0.1 * torch.randn(64, generator=gen)
+    rc = r.clone().requires_grad_(True)
+    y_ref = rc * torch.rsqrt(rc.pow(2).mean(-1, keepdim=True) + 1e-5) * w
+    y_ref.sum().backward()
+    for T in (torch.float32, torch.bfloat16):
+        rg = r.cuda().requires_grad_(True)
+        y, s = ops.rmsnorm_fn(None, w.cuda(), rg, 1e-5, T)
+        assert s is rg and y.dtype == T
+        y.float().sum().backward()
+        tol = (RTOL32, 1e-5) if T == torch.float32 else (RTOL16, FLOOR16)
+        assert_close(y, y_ref, *tol, what=f"rmsnorm first-layer y {T}")
+        assert rg.grad.dtype == torch.float32
+        assert_close(rg.grad, rc.grad, *tol, what=f"rmsnorm first-layer dres {T}")
+
+
+# ---------------------------------------------------------------------------------------------------
+# decode step kernels
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cfg", [(2, 64, 16, 4, 4), (5, 96, 64, 4, 6), (1, 40, 5, 3, 3)])
+def test_conv_and_ssm_step_match_oracle_recurrence(cfg):
+    from mamba_b200 import ops
+    B, D, N, K, R = cfg
+    gen = torch.Generator().manual_seed(D)
+    w = torch.randn(D, K, generator=gen) * 0.5
+    cb = torch.randn(D, generator=gen) * 0.1
+    dtw = torch.randn(D, R, generator=gen) * 0.3
+    dtb = torch.randn(D, generator=gen) * 0.3 - 3
+    A = -torch.rand(D, N, generator=gen) - 0.2
+    Dv = torch.randn(D, generator=gen)
+    conv_ref = torch.zeros(B, D, K)
+    h_ref = torch.zeros(B, D, N)
+    conv_g = torch.zeros(B, D, K, device="cuda")
+    h_g = torch.zeros(B, D, N, device="cuda")
+    for t in range(6):
+        x = torch.randn(B, D, generator=gen)
+        dt_in = torch.randn(B, R, generator=gen)
+        Bv = torch.randn(B, N, generator=gen)
+        Cv = torch.randn(B, N, generator=gen)
+        z = torch.randn(B, D, generator=gen)
+        conv_ref = torch.cat((conv_ref[:, :, 1:], x[:, :, None]), dim=-1)
+        xc_ref = F.silu((conv_ref * w).sum(-1) + cb)
+        delta = F.softplus(dt_in @ dtw.T + dtb)
+        h_ref = torch.exp(delta[:, :, None] * A) * h_ref + (delta * xc_ref)[:, :, None] * Bv[:, None, :]
+        y_ref = ((h_ref * Cv[:, None, :]).sum(-1) + Dv * xc_ref) * F.silu(z)
+        xc = ops.conv_step(x.cuda(), conv_g, w.cuda(), cb.cuda())
+        assert_close(xc, xc_ref, RTOL32, what=f"conv_step t={t}")
+        y = ops.ssm_step(xc, dt_in.cuda(), Bv.cuda(), Cv.cuda(), dtw.cuda(), dtb.cuda(), A.cuda(), Dv.cuda(), z.cuda(), h_g)
+        assert_close(y, y_ref, RTOL32, what=f"ssm_step y t={t}")
+        assert_close(h_g, h_ref, RTOL32, what=f"ssm_step h t={t}")
+        assert torch.equal(conv_g.cpu(), conv_ref)

@@ -1,0 +1,189 @@
+"""GPU parity tests at module level: MambaBlock / Mamba (both layouts), the training step and the decode
+paths against the CPU oracle on identical weights and inputs (fp32 rtol 1e-4; bf16 tolerance stated below)."""
+import pytest
+import torch
+
+from oracle import simple_mamba as om
+from oracle import train_ref
+from util import assert_close
+
+pytestmark = pytest.mark.gpu
+
+RTOL32 = 1e-4
+
+
+def _args(cls, **kw):
+    from mamba_b200.configs import common as cc
+    base = dict(d_model=64, n_layer=2, vocab_size=cc.vocab_size, d_state=16, expand=2, d_conv=4,
+                pad_vocab_size_multiple=1, metadata_vocab_size=cc.metadata_vocab_size)
+    base.update(kw)
+    return cls(**base)
+
+
+def _randomise(module, seed):
+    """Move every parameter off its init so that A_log, D, biases and norms all matter."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, p in module.named_parameters():
+            if name.endswith("A_log"):
+                p.add_(0.2 * torch.randn(p.shape, generator=g))
+            elif name.endswith("dt_proj.bias"):
+                p.copy_(torch.randn(p.shape, generator=g) * 0.5 - 3.0)
+            elif p.dim() == 1:
+                p.add_(0.1 * torch.randn(p.shape, generator=g))
+            else:
+                p.add_(0.02 * torch.randn(p.shape, generator=g))
+
+
+@pytest.mark.parametrize("cfg", [dict(d_model=64, d_state=16), dict(d_model=48, d_state=64), dict(d_model=256, d_state=64)])
+@pytest.mark.parametrize("L", [1, 37, 300])
+def test_mamba_block_forward_backward_fp32(cfg, L):
+    from mamba_b200.models.mamba import MambaBlock, ModelArgs
+    torch.manual_seed(0)
+    ref = om.MambaBlock(_args(om.ModelArgs, **cfg))
+    _randomise(ref, 1)
+    blk = MambaBlock(_args(ModelArgs, **cfg)).cuda()
+    blk.load_state_dict(ref.state_dict(), strict=True)
+    x = torch.randn(2, L, cfg["d_model"])
+    dy = torch.randn(2, L, cfg["d_model"])
+    xc = x.clone().requires_grad_(True)
+    yr = ref(xc)
+    yr.backward(dy)
+    xg = x.cuda().requires_grad_(True)
+    yg = blk(xg)
+    yg.backward(dy.cuda())
+    assert_close(yg, yr, RTOL32, what="block fwd")
+    assert_close(xg.grad, xc.grad, RTOL32, what="block dx")
+    gp = dict(blk.named_parameters())
+    for name, p in ref.named_parameters():
+        assert_close(gp[name].grad, p.grad, RTOL32, 2e-5, what=f"block d{name}")
+
+
+@pytest.mark.parametrize("layout", ["P", "S"])
+def test_model_logits_loss_and_grads_fp32(layout):
+    """Full model through the reference loss (filtered_logit + CrossEntropy): logits, loss, every gradient."""
+    from mamba_b200 import synthetic, train
+    from mamba_b200.models.mamba import Mamba, ModelArgs
+    torch.manual_seed(0)
+    if layout == "P":
+        ref = om.Mamba(_args(om.ModelArgs))
+        model = Mamba(_args(ModelArgs))
+    else:
+        ref = om.ShippedWrapper(_args(om.ModelArgs), d_model=64, n_layers=2)
+        model = Mamba(d_model=64, n_layers=2)
+        # the shipped-signature constructor reads d_state etc. from configs: rebuild the oracle to match
+        ref = om.ShippedWrapper(om.ModelArgs(d_model=64, n_layer=2, vocab_size=17914, d_state=model.params.d_state,
+                                             expand=2, d_conv=4, pad_vocab_size_multiple=1), d_model=64, n_layers=2)
+    _randomise(ref, 2)
+    model.load_state_dict(ref.state_dict(), strict=True)
+    model.cuda()
+    src, trg, meta = synthetic.batch(2, 45, seed=5)
+    lr = ref(src, meta)
+    loss_r = train_ref.loss_fn(src, trg, lr)
+    loss_r.backward()
+    lg = model(src.cuda(), meta.cuda())
+    loss_g = train.loss_fn(src.cuda(), trg.cuda(), lg)
+    loss_g.backward()
+    assert lg.shape == lr.shape == (2, 45, 17914)
+    assert_close(lg, lr, RTOL32, what=f"{layout} logits")
+    assert abs(loss_g.item() - loss_r.item()) <= 1e-4 * abs(loss_r.item())
+    gp = dict(model.named_parameters())
+    for name, p in ref.named_parameters():
+        assert_close(gp[name].grad, p.grad, RTOL32, 2e-5, what=f"{layout} d{name}")
+
+
+def test_model_bf16_autocast_tolerance():
+    """bf16 mixer / fp32 residual stream under autocast vs the fp32 oracle: logits within 3e-2 of max|logit|
+    (stated bf16 tolerance: two layers of bf16 GEMMs with 2^-9 input rounding each)."""
+    from mamba_b200 import synthetic
+    from mamba_b200.models.mamba import Mamba, ModelArgs
+    torch.manual_seed(0)
+    ref = om.Mamba(_args(om.ModelArgs))
+    _randomise(ref, 3)
+    model = Mamba(_args(ModelArgs))
+    model.load_state_dict(ref.state_dict())
+    model.cuda()
+    src, trg, meta = synthetic.batch(2, 64, seed=6)
+    with torch.no_grad():
+        lr = ref(src, meta)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            lg = model(src.cuda(), meta.cuda())
+    assert lg.dtype == torch.bfloat16
+    err = (lg.float().cpu() - lr).abs().max().item()
+    assert err <= 3e-2 * lr.abs().max().item(), err
+
+
+def test_state_dict_roundtrip_on_gpu(tmp_path):
+    from mamba_b200.models.mamba import Mamba, ModelArgs
+    m1 = Mamba(_args(ModelArgs)).cuda()
+    torch.save(m1.state_dict(), tmp_path / "m.pth")       # train.py:77
+    m2 = Mamba(_args(ModelArgs)).cuda()
+    m2.load_state_dict(torch.load(tmp_path / "m.pth"), strict=True)  # train.py:66
+    for (k1, v1), (k2, v2) in zip(m1.state_dict().items(), m2.state_dict().items()):
+        assert k1 == k2 and torch.equal(v1, v2)
+
+
+def test_prefill_and_step_match_full_forward():
+    """Row A9: prefill == forward, and stepping token by token reproduces the forward logits position by position."""
+    from mamba_b200 import synthetic
+    from mamba_b200.models.mamba import Mamba, ModelArgs
+    torch.manual_seed(0)
+    ref = om.Mamba(_args(om.ModelArgs))
+    _randomise(ref, 4)
+    model = Mamba(_args(ModelArgs))
+    model.load_state_dict(ref.state_dict())
+    model.cuda().eval()
+    src, _, meta = synthetic.batch(3, 40, seed=7)
+    with torch.no_grad():
+        full_ref = ref(src, meta)
+        full = model(src.cuda(), meta.cuda())
+        cache = model.allocate_inference_cache(3)
+        pre = model.prefill(src[:, :25].cuda(), meta.cuda(), cache)
+        assert_close(pre, full_ref[:, :25], RTOL32, what="prefill logits")
+        assert torch.equal(pre, full[:, :25])
+        for t in range(25, 40):
+            lg = model.step(src[:, t].cuda(), cache)
+            assert_close(lg, full_ref[:, t], RTOL32, 2e-5, what=f"step logits t={t}")
+
+
+def test_greedy_decode_tokens_match_oracle():
+    """Greedy decode (scripts/generate_midi_many.py:13-56): literal loop on the kernels, recurrent decoder and
+    the oracle loop produce the same token sequence.  Positions whose top-2 margin is below 1e-4 relative are
+    reported and not counted as failures (different summation orders)."""
+    from mamba_b200 import generate, synthetic
+    from mamba_b200.models.mamba import Mamba, ModelArgs
+    torch.manual_seed(0)
+    ref = om.Mamba(_args(om.ModelArgs)).eval()
+    _randomise(ref, 5)
+    model = Mamba(_args(ModelArgs))
+    model.load_state_dict(ref.state_dict())
+    model.cuda().eval()
+    src, _, meta = synthetic.batch(2, 120, seed=8)
+    n_new = 24
+    want = [train_ref.generate_greedy(ref, 4096, src[i:i + 1].clone(), meta[i:i + 1], n_new) for i in range(2)]
+    want = torch.tensor(want)
+    lit = generate.generate_literal(model, 4096, src.cuda(), meta.cuda(), n_new).cpu()
+    rec = generate.generate_recurrent(model, src.cuda(), meta.cuda(), n_new, use_graph=True).cpu()
+    rec_nograph = generate.generate_recurrent(model, src.cuda(), meta.cuda(), n_new, use_graph=False).cpu()
+    assert torch.equal(rec, rec_nograph)
+    assert torch.equal(lit, want), (lit[:, 120:], want[:, 120:])
+    assert torch.equal(rec, want), (rec[:, 120:], want[:, 120:])
+
+
+def test_trainer_graph_step_equals_eager_step():
+    """The CUDA-graphed step (Trainer) and the python-launched reference-shaped step produce the same losses."""
+    from mamba_b200 import synthetic, train
+    from mamba_b200.models.mamba import Mamba, ModelArgs
+    torch.manual_seed(0)
+    a = Mamba(_args(ModelArgs)).cuda()
+    b = Mamba(_args(ModelArgs)).cuda()
+    b.load_state_dict(a.state_dict())
+    opt = torch.optim.Adam(a.parameters(), lr=1e-3)
+    tr = train.Trainer(b, lr=1e-3, autocast_dtype=None, batch_size=2, block_len=48, use_graph=True)
+    for i in range(4):
+        src, trg, meta = (t.cuda() for t in synthetic.batch(2, 48, seed=20 + i))
+        la = train.train_step(a, opt, src, trg, meta)
+        lb = tr.step(src, trg, meta)
+        assert abs(la.item() - lb.item()) <= 2e-4 * abs(la.item()), (i, la.item(), lb.item())
+    for (n1, p1), (n2, p2) in zip(a.named_parameters(), b.named_parameters()):
+        assert_close(p2, p1, 1e-3, 1e-4, what=f"param {n1} after 4 steps")

@@ -1,0 +1,88 @@
+"""CPU tests of the host-side mirror of the reference interface (configs, loss path, synthetic data,
+module construction / state_dict layout)."""
+import torch
+
+from mamba_b200 import synthetic, train
+from mamba_b200.configs import common as cc
+from mamba_b200.models.mamba import Mamba, MambaBlock, ModelArgs
+from oracle import simple_mamba as om
+from oracle import train_ref
+
+
+def test_config_values_match_reference():
+    V, s = train_ref.vocab_layout()
+    assert cc.vocab_size == V == 17914
+    assert cc.start_idx == s
+    assert cc.metadata_vocab_size == 568
+    assert cc.config.values.block_len == 2048 and cc.config.values.batch_size == 2
+    assert cc.config.values.learning_rate == 5e-5
+    d = train.get_mamba_dict()
+    assert (d.d_model, d.n_layer, d.d_state, d.expand, d.d_conv, d.d_inner, d.dt_rank) == (1024, 10, 64, 2, 4, 2048, 64)
+    assert train.get_mamba_dict(pad_vocab=True).vocab_size == 17920 == train.get_actual_vocab_size("mamba")
+
+
+def test_loss_path_matches_oracle_on_cpu():
+    torch.manual_seed(0)
+    src, trg, _ = synthetic.batch(2, 32, seed=3)
+    out = torch.randn(2, 32, cc.vocab_size)
+    assert torch.equal(train.make_distributions("cpu"), train_ref.make_distributions())
+    assert torch.equal(train.pick_distributions_by_prev_token(src), train_ref.pick_distributions_by_prev_token(src))
+    assert torch.equal(train.filtered_logit(src, out), train_ref.filtered_logit(src, out))
+    assert torch.equal(train.loss_fn(src, trg, out), train_ref.loss_fn(src, trg, out))
+
+
+def test_synthetic_batch_follows_grammar():
+    src, trg, meta = synthetic.batch(3, 50, seed=1)
+    assert src.shape == trg.shape == (3, 50) and meta.shape == (3, 6)
+    assert torch.equal(src[:, 1:], trg[:, :-1])
+    s = cc.start_idx
+    bounds = [s["pitch"], s["dyn"], s["length"], s["time"], s["tempo"], cc.vocab_size]
+    for p in range(50):
+        c = p % 5
+        assert (src[:, p] >= bounds[c]).all() and (src[:, p] < bounds[c + 1]).all()
+    assert (meta[:, 0] >= 313).all() and (meta[:, 0] <= 567).all()
+    assert (meta[:, 1:5] >= 203).all() and (meta[:, 1:5] <= 311).all()
+    assert (meta[:, 5] >= 1).all() and (meta[:, 5] <= 201).all()
+    again = synthetic.batch(3, 50, seed=1)
+    assert torch.equal(src, again[0]) and torch.equal(meta, again[2])
+
+
+def _small_args(cls):
+    return cls(d_model=32, n_layer=2, vocab_size=cc.vocab_size, d_state=8, expand=2, d_conv=4,
+               pad_vocab_size_multiple=1, metadata_vocab_size=cc.metadata_vocab_size)
+
+
+def test_state_dict_layout_matches_oracle_layout_p():
+    prod = Mamba(_small_args(ModelArgs))
+    ref = om.Mamba(_small_args(om.ModelArgs))
+    sp, sr = prod.state_dict(), ref.state_dict()
+    assert list(sp.keys()) == list(sr.keys())
+    for k in sp:
+        assert sp[k].shape == sr[k].shape and sp[k].dtype == sr[k].dtype, k
+    ref.load_state_dict(sp, strict=True)
+    prod.load_state_dict(ref.state_dict(), strict=True)
+    assert prod.lm_head.weight is prod.embedding.weight  # tied (simple_mamba @L70)
+
+
+def test_state_dict_layout_shipped_wrapper():
+    m = Mamba(d_model=32, n_layers=2)
+    keys = list(m.state_dict().keys())
+    assert keys[:4] == ["token_embedding.weight", "metadata_embedding.weight", "output_layer.weight",
+                        "output_layer.bias"]
+    assert "layers.1.out_proj.weight" in keys and keys[-2:] == ["norm.weight", "norm.bias"]
+    ref = om.ShippedWrapper(_small_args(om.ModelArgs), d_model=32, n_layers=2)
+    assert list(ref.state_dict().keys()) == keys
+    assert m.token_embedding.weight.shape == (17914, 32)
+
+
+def test_block_init_matches_reference_init():
+    blk = MambaBlock(_small_args(ModelArgs))
+    assert torch.equal(blk.A_log, torch.log(torch.arange(1, 9, dtype=torch.float32)).repeat(64, 1))
+    assert torch.equal(blk.D, torch.ones(64))
+    assert blk.conv1d.weight.shape == (64, 1, 4) and blk.x_proj.weight.shape == (2 + 16, 64)
+    assert blk.in_proj.bias is None and blk.dt_proj.bias is not None
+
+
+def test_default_model_param_count():
+    m = train.new_model("mamba")
+    assert sum(p.numel() for p in m.parameters()) == 88554496 - 6 * 1024  # unpadded vocabulary
