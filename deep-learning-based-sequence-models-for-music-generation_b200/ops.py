@@ -12,7 +12,7 @@ new token (no reference counterpart: scripts/generate.py:26-31 re-runs the full 
 """
 from __future__ import annotations
 
-import ctypes as C
+import ctypes as ct
 import os
 
 import torch
@@ -50,17 +50,34 @@ def _rows(t: torch.Tensor) -> torch.Tensor:
 
 
 def _p(t):
-    return None if t is None else C.c_void_p(t.data_ptr())
+    return None if t is None else ct.c_void_p(t.data_ptr())
 
 
-def _stream() -> C.c_void_p:
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream() -> ct.c_void_p:
+    return ct.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
 def _f32(t):
     if t is None:
         return None
     return t.detach().to(torch.float32).contiguous()
+
+
+# Optional per-op device timing (bench.py's roofline leg): when KERNEL_TIMES is a dict, every C-ABI call is
+# bracketed by CUDA events on the launching stream and the (start, end) pairs are collected per entry point.
+KERNEL_TIMES = None
+
+
+def _call(name, a, dev):
+    with torch.cuda.device(dev):
+        if KERNEL_TIMES is None:
+            check(getattr(lib(), name)(ct.byref(a), _stream()), name)
+            return
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(getattr(lib(), name)(ct.byref(a), _stream()), name)
+        e1.record()
+        KERNEL_TIMES.setdefault(name, []).append((e0, e1))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -72,7 +89,7 @@ def _scan_fwd_raw(u, delta, A, B, C, D, z, delta_bias, delta_softplus, ckpt, chu
     N = A.shape[1]
     out = torch.empty((Bsz, L, Dm), dtype=u.dtype, device=u.device)
     a = ScanFwdArgs()
-    a.struct_size = C.sizeof(ScanFwdArgs)
+    a.struct_size = ct.sizeof(ScanFwdArgs)
     a.dtype = _dtype_code(u)
     a.batch, a.seqlen, a.dim, a.dstate = Bsz, L, Dm, N
     a.chunk = chunk
@@ -92,8 +109,7 @@ def _scan_fwd_raw(u, delta, A, B, C, D, z, delta_bias, delta_softplus, ckpt, chu
     a.ckpt = _p(ckpt)
     a.h_last = _p(h_last)
     a.h_init = _p(h_init)
-    with torch.cuda.device(u.device):
-        check(lib().mamba_scan_fwd(C.byref(a), _stream()), "mamba_scan_fwd")
+    _call("mamba_scan_fwd", a, u.device)
     return out
 
 
@@ -142,7 +158,7 @@ class SelectiveScanFn(torch.autograd.Function):
         wsb = lib().mamba_scan_bwd_workspace_bytes(Bsz, L, Dm, N)
         ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
         a = ScanBwdArgs()
-        a.struct_size = C_sizeof(ScanBwdArgs)
+        a.struct_size = ct.sizeof(ScanBwdArgs)
         a.dtype = _dtype_code(u)
         a.batch, a.seqlen, a.dim, a.dstate = Bsz, L, Dm, N
         a.chunk = ctx.chunk
@@ -167,14 +183,12 @@ class SelectiveScanFn(torch.autograd.Function):
         a.dC, a.dC_bs, a.dC_ls = _p(dC), dC.stride(0), dC.stride(1)
         a.dA, a.dD, a.ddelta_bias = _p(dA), _p(dD), _p(ddb)
         a.workspace, a.workspace_bytes = _p(ws), wsb
-        with torch.cuda.device(dev):
-            check(lib().mamba_scan_bwd(C.byref(a), _stream()), "mamba_scan_bwd")
+        _call("mamba_scan_bwd", a, dev)
         tA, tD, tb = ctx.in_dtypes
         return (du, ddelta, dA.to(tA), dB, dC, None if dD is None else dD.to(tD), dz,
                 None if ddb is None else ddb.to(tb), None, None)
 
 
-C_sizeof = C.sizeof
 
 
 def selective_scan_fn(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus=False, chunk=None):
@@ -202,7 +216,7 @@ def selective_scan_prefill(u, delta, A, B, C, D=None, z=None, delta_bias=None, d
 # ------------------------------------------------------------------------------------------------
 def _conv_args(x, w2, bias, K):
     a = ConvArgs()
-    a.struct_size = C.sizeof(ConvArgs)
+    a.struct_size = ct.sizeof(ConvArgs)
     a.dtype = _dtype_code(x)
     a.batch, a.seqlen, a.dim, a.width = x.shape[0], x.shape[1], x.shape[2], K
     a.x, a.x_bs, a.x_ls = _p(x), x.stride(0), x.stride(1)
@@ -224,8 +238,7 @@ class CausalConv1dSiluFn(torch.autograd.Function):
         out = torch.empty((x.shape[0], x.shape[1], D), dtype=x.dtype, device=x.device)
         a = _conv_args(x, w2, b32, K)
         a.out, a.out_bs, a.out_ls = _p(out), out.stride(0), out.stride(1)
-        with torch.cuda.device(x.device):
-            check(lib().mamba_conv1d_silu_fwd(C.byref(a), _stream()), "mamba_conv1d_silu_fwd")
+        _call("mamba_conv1d_silu_fwd", a, x.device)
         ctx.save_for_backward(x, w2, b32)
         ctx.wshape = weight.shape
         ctx.wdtype = weight.dtype
@@ -248,8 +261,7 @@ class CausalConv1dSiluFn(torch.autograd.Function):
         a.dx, a.dx_bs, a.dx_ls = _p(dx), dx.stride(0), dx.stride(1)
         a.dweight, a.dbias = _p(dw), _p(db)
         a.workspace, a.workspace_bytes = _p(ws), wsb
-        with torch.cuda.device(x.device):
-            check(lib().mamba_conv1d_silu_bwd(C.byref(a), _stream()), "mamba_conv1d_silu_bwd")
+        _call("mamba_conv1d_silu_bwd", a, x.device)
         return dx, dw.view(ctx.wshape).to(ctx.wdtype), None if db is None else db.to(ctx.bdtype)
 
 
@@ -269,8 +281,7 @@ def causal_conv1d_silu_prefill(x, weight, bias=None):
     a = _conv_args(x, w2, b32, K)
     a.out, a.out_bs, a.out_ls = _p(out), out.stride(0), out.stride(1)
     a.final_state = _p(state)
-    with torch.cuda.device(x.device):
-        check(lib().mamba_conv1d_silu_fwd(C.byref(a), _stream()), "mamba_conv1d_silu_fwd")
+    _call("mamba_conv1d_silu_fwd", a, x.device)
     return out, state
 
 
@@ -279,7 +290,7 @@ def causal_conv1d_silu_prefill(x, weight, bias=None):
 # ------------------------------------------------------------------------------------------------
 def _norm_args(act_dtype, resid_dtype, rows, dim, eps):
     a = NormArgs()
-    a.struct_size = C.sizeof(NormArgs)
+    a.struct_size = ct.sizeof(NormArgs)
     a.dtype = _DTYPES[act_dtype]
     a.resid_dtype = _DTYPES[resid_dtype]
     a.rows, a.dim, a.eps = rows, dim, eps
@@ -311,8 +322,7 @@ class RMSNormFn(torch.autograd.Function):
         a = _norm_args(T, TR, rows, dim, eps)
         a.x, a.residual, a.weight = _p(x2), _p(r2), _p(w32)
         a.y, a.resid_out, a.rstd = _p(y), _p(ro), _p(rstd)
-        with torch.cuda.device(dev):
-            check(lib().mamba_rmsnorm_fwd(C.byref(a), _stream()), "mamba_rmsnorm_fwd")
+        _call("mamba_rmsnorm_fwd", a, dev)
         normed = ro if ro is not None else (r2 if r2 is not None else x2)
         ctx.save_for_backward(normed, w32, rstd)
         ctx.meta = (T, TR, eps, shape, weight.dtype, x is not None, residual is not None)
@@ -345,8 +355,7 @@ class RMSNormFn(torch.autograd.Function):
         else:
             a.dx, a.dresid_out = _p(dx), _p(dro)
         a.workspace, a.workspace_bytes = _p(ws), wsb
-        with torch.cuda.device(dev):
-            check(lib().mamba_rmsnorm_bwd(C.byref(a), _stream()), "mamba_rmsnorm_bwd")
+        _call("mamba_rmsnorm_bwd", a, dev)
         gx = dx.view(shape) if has_x else None
         if has_res:
             gr = (dro if dro is not None else dx).view(shape)
@@ -371,7 +380,7 @@ def rmsnorm_fn(x, weight, residual=None, eps=1e-5, act_dtype=None):
 # ------------------------------------------------------------------------------------------------
 def _step_args(dtype_t, Bsz, D, N, K, R, flags):
     a = StepArgs()
-    a.struct_size = C.sizeof(StepArgs)
+    a.struct_size = ct.sizeof(StepArgs)
     a.dtype = _dtype_code(dtype_t)
     a.batch, a.dim, a.dstate, a.width, a.dt_rank, a.flags = Bsz, D, N, K, R, flags
     return a
@@ -389,8 +398,7 @@ def conv_step(x, conv_state, weight2d, bias):
     a.x, a.x_bs = _p(x), x.stride(0)
     a.conv_state, a.conv_weight, a.conv_bias = _p(conv_state), _p(weight2d), _p(bias)
     a.xc, a.xc_bs = _p(xc), xc.stride(0)
-    with torch.cuda.device(x.device):
-        check(lib().mamba_conv_step(C.byref(a), _stream()), "mamba_conv_step")
+    _call("mamba_conv_step", a, x.device)
     return xc
 
 
@@ -416,8 +424,7 @@ def ssm_step(xc, dt_in, Bv, Cv, dt_weight, dt_bias, A, D, z, ssm_state, delta_so
         a.z, a.z_bs = _p(z), z.stride(0)
     a.ssm_state = _p(ssm_state)
     a.y, a.y_bs = _p(y), y.stride(0)
-    with torch.cuda.device(xc.device):
-        check(lib().mamba_ssm_step(C.byref(a), _stream()), "mamba_ssm_step")
+    _call("mamba_ssm_step", a, xc.device)
     return y
 
 

@@ -170,6 +170,9 @@ class Trainer:
         self.loss.copy_(loss.detach())
 
     def capture(self, warmup=3):
+        """Warm up on a side stream, capture one step, then put parameters and Adam state back to where they
+        were: capturing must not train."""
+        saved = [p.detach().clone() for p in self.model.parameters()]
         s = torch.cuda.Stream(device=self.device)
         s.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(s):
@@ -180,6 +183,14 @@ class Trainer:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self._step_body()
+        with torch.no_grad():
+            for p, q in zip(self.model.parameters(), saved):
+                p.copy_(q)
+            for st in self.optimizer.state.values():   # exp_avg, exp_avg_sq and the device-side step counter
+                for v in st.values():
+                    if torch.is_tensor(v):
+                        v.zero_()
+        torch.cuda.synchronize(self.device)
 
     def step(self, src, trg, meta):
         """src/trg/meta: host (pinned) or device tensors of the configured shape.  Returns the device-side

@@ -68,8 +68,9 @@ def test_scan_forward_flag_combinations(flags):
     from mamba_b200 import ops
     has_z, has_D, has_bias, softplus = flags
     t = scan_inputs(2, 50, 64, 16, seed=2)
-    if not softplus:
-        t["delta_raw"] = F.softplus(t["delta_raw"])  # a positive step either way
+    if not softplus:  # keep the step positive either way (a negative step makes the recurrence diverge)
+        t["delta_raw"] = F.softplus(t["delta_raw"])
+        t["bias"] = t["bias"].abs()
     ref = _oracle_scan(t, has_z, has_D, has_bias, softplus)
     g = {k: v.cuda() for k, v in t.items()}
     out = ops.selective_scan_fn(g["u"], g["delta_raw"], g["A"], g["B"], g["C"], g["D"] if has_D else None,
@@ -259,7 +260,7 @@ def test_conv1d_bf16():
     w = torch.randn(D, 1, K, generator=gen) * 0.5
     b = torch.randn(D, generator=gen) * 0.1
     dout = torch.randn(B, L, D, generator=gen).bfloat16()
-    xc, wc, bc = x.float().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    xc, wc, bc = (v.float().clone().requires_grad_(True) for v in (x, w, b))
     ref = _oracle_conv(xc, wc, bc)
     ref.backward(dout.float())
     xg, wg, bg = x.cuda().requires_grad_(True), w.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
@@ -310,8 +311,7 @@ def test_rmsnorm_fused_residual(dtypes):
     w = 1 + 0.1 * torch.randn(128, generator=gen)
     dy = torch.randn(2, 11, 128, generator=gen).to(T)
     ds = torch.randn(2, 11, 128, generator=gen).to(TR)
-    xc, rc, wc = x.float().requires_grad_(True), r.float().requires_grad_(True), w.clone().requires_grad_(True)
-    s_ref = (xc + rc).to(TR).float() if TR != torch.float32 else xc + rc
+    xc, rc, wc = (v.float().clone().requires_grad_(True) for v in (x, r, w))
     s_ref = xc + rc
     y_ref = s_ref * torch.rsqrt(s_ref.pow(2).mean(-1, keepdim=True) + 1e-5) * wc
     (y_ref * dy.float()).sum().backward(retain_graph=True)

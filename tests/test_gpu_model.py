@@ -88,7 +88,13 @@ def test_model_logits_loss_and_grads_fp32(layout):
     assert_close(lg, lr, RTOL32, what=f"{layout} logits")
     assert abs(loss_g.item() - loss_r.item()) <= 1e-4 * abs(loss_r.item())
     gp = dict(model.named_parameters())
+    gmax = max(float(p.grad.abs().max()) for p in ref.parameters())
     for name, p in ref.named_parameters():
+        if float(p.grad.abs().max()) < 1e-6 * gmax:
+            # mathematically zero (e.g. output_layer.bias: the sequence-axis log_softmax of F4 removes any
+            # per-vocab constant) — both sides hold rounding noise only
+            assert float(gp[name].grad.abs().max()) < 1e-5 * gmax, name
+            continue
         assert_close(gp[name].grad, p.grad, RTOL32, 2e-5, what=f"{layout} d{name}")
 
 
