@@ -1,27 +1,35 @@
-// scan_fwd.cu — fused selective-scan forward for sm_100a.
+// scan_fwd.cu — fused selective-scan forward for sm_100a (warp-specialised, MUFU-paced).
 //
 // Replaces MambaBlock.selective_scan (reference models/mamba/__pycache__/simple_mamba.cpython-311.pyc
 // @L310-333) fused with softplus(dt) (@L276), the D skip (@L331) and the z gate (@L241).
 //
-// Mapping (B200-first, not the reference's python loop over L):
-//   * one CTA owns (batch b, 32 consecutive channels); lane <-> channel d, warp <-> slice of NPER
-//     states n.  Every global access of u/delta/z/out is therefore a fully coalesced 128-byte row.
-//   * the state h[NPER] lives in registers for the whole sequence; the CTA walks L sequentially in
-//     stages of LCS timesteps that are double-buffered into shared memory with cp.async (16-byte
-//     LDGSTS), so HBM latency is hidden behind the recurrence of the previous stage.
-//   * per stage: a cooperative pre-pass turns raw delta into softplus(delta+bias) and delta*u once
-//     per (t, d) (not once per state), the main loop does exp2/FMA per (t, d, n), and a cooperative
-//     post-pass reduces the per-warp partial <h, C> sums, adds D*u, applies silu(z) and stores.
-//   * every CK timesteps the state is checkpointed to HBM ([B, nck, N, D], coalesced) so the
-//     backward can recompute the forward chunk by chunk.  deltaA / deltaB_u ([B, L, D, N] in the
-//     reference) never exist in memory.
+// The op is one ex2 per (b, t, d, n) on the MUFU pipe (16 lanes/clk/SM measured, tools/microbench.cu) plus four
+// fp32 multiply-adds; at d_state 64 that is ~6x more time than its HBM traffic, at d_state 16 about 1.4x.  The
+// kernel is organised so that the MUFU pipe is the only thing that is ever busy:
+//   * one CTA owns (batch b, 32 consecutive channels) for the whole sequence; lane <-> channel, so every global
+//     access of u / delta / z / out is a coalesced row and no shuffle is ever needed.
+//   * SCAN warps (one per slice of NPER states) do nothing but the recurrence.  Per timestep: one 8-byte LDS of
+//     (delta, delta*u), broadcast 16-byte LDS of B and C, and per PAIR of states {FMUL2, 2 x MUFU.EX2, FMUL2,
+//     FFMA2, FFMA2} using Blackwell's packed fp32x2 pipe ops (3 issue slots per state instead of 5), then one
+//     STS of the partial <h, C>.  h[NPER] stays in registers for all L steps; operands of step t+1 are fetched
+//     before step t is computed.
+//   * HELPER warps (4) run everything else through shared-memory rings: cp.async (LDGSTS, 16 B) loads RR stages
+//     ahead (enough bytes in flight to cover HBM latency with one CTA per SM), the pre-pass (softplus(delta +
+//     bias), delta*u; bf16 -> fp32 B/C), and the post-pass (sum of the per-warp partials, + D*u, * silu(z),
+//     128-bit coalesced store).  Each helper thread owns (timestep, 4 consecutive channels) of a stage.
+//   * producer/consumer hand-off uses named barriers (bar.arrive / bar.sync), two per work slot.
+//   * every 16 timesteps the scan warps checkpoint h to HBM ([B, nck, N, D], coalesced) for the backward.
+//     deltaA / deltaB_u ([B, L, D, N] in the reference) never exist in memory.
 #include "common.cuh"
 
 namespace mb {
 
 constexpr int kDT = 32;   // channels per CTA (= warp width)
-constexpr int kLCS = 32;  // timesteps per shared-memory stage
-constexpr int kMaxWarps = 16;  // state slices per CTA (<= 512 threads, <= 128 registers each)
+constexpr int kTS = 16;   // timesteps per stage (= checkpoint interval)
+constexpr int kHelperWarps = 4;
+constexpr int kHelperThreads = kHelperWarps * 32;
+constexpr int kMaxScanWarps = 16;
+constexpr int kMaxBCVec = 4;  // precomputed B/C cp.async slots per helper thread (fast path)
 
 struct ScanFwdParams {
   int B, L, D, N, NS, NPT, nck, flags;
@@ -33,46 +41,198 @@ struct ScanFwdParams {
   int vec_u, vec_delta, vec_z, vec_B, vec_C, vec_out;
 };
 
+// ---- fast transcendental helpers (MUFU ex2 / lg2 / rcp; relative error ~1e-7, far inside rtol 1e-4) ----------
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// softplus with torch's threshold (x > 20 -> x).  For x < -4 the series of log1p(e) avoids the cancellation
+// of forming 1 + e in fp32.
+__device__ __forceinline__ float softplus_fast(float x) {
+  const float e = ex2_approx(x * kLog2e);
+  const float series = e * fmaf(e, fmaf(e, fmaf(e, -0.25f, 0.33333334f), -0.5f), 1.f);
+  const float full = lg2_approx(1.f + e) * kLn2;
+  const float r = x < -4.f ? series : full;
+  return x > 20.f ? x : r;
+}
+__device__ __forceinline__ float silu_fast(float x) { return x * rcp_approx(1.f + ex2_approx(-x * kLog2e)); }
+
+// Shared-memory store issued through asm so that nvvm does not order later shared loads behind it.
+__device__ __forceinline__ void sts_f32(float* p, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "f"(v));
+}
+__device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int count) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+// 4 consecutive elements of T <-> 4 floats
 template <typename T>
-struct FwdSmem {
-  // raw (cp.async targets), per stage
-  T *u, *dl, *z, *Bm, *Cm;
+struct V4;
+template <>
+struct V4<float> {
+  static __device__ __forceinline__ void ld(const float* p, float (&v)[4]) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w;
+  }
+  static __device__ __forceinline__ void st_global(float* p, const float (&v)[4]) { st_cs_f4(p, make_float4(v[0], v[1], v[2], v[3])); }
+};
+template <>
+struct V4<__nv_bfloat16> {
+  static __device__ __forceinline__ void ld(const __nv_bfloat16* p, float (&v)[4]) {
+    const uint2 t = *reinterpret_cast<const uint2*>(p);
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&t.x);
+    const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&t.y);
+    v[0] = __low2float(a), v[1] = __high2float(a), v[2] = __low2float(b), v[3] = __high2float(b);
+  }
+  static __device__ __forceinline__ void st_global(__nv_bfloat16* p, const float (&v)[4]) {
+    const __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+    uint2 t;
+    t.x = *reinterpret_cast<const uint32_t*>(&a), t.y = *reinterpret_cast<const uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = t;
+  }
 };
 
-template <typename T, int NPER, int CK>
-__global__ void __launch_bounds__(kMaxWarps * 32) scan_fwd_kernel(const ScanFwdParams p) {
-  static_assert(kLCS % CK == 0, "stage must hold whole checkpoint chunks");
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int tid = threadIdx.x, lane = tid & 31, s = tid >> 5;
-  const int nthreads = blockDim.x;
-  const int b = blockIdx.y;
-  const int d0 = blockIdx.x * kDT;
-  const int d = d0 + lane;
+// Shared-memory layout.  RAW ring slot (cp.async targets, element type T):
+//     u[TS][32], delta[TS][32], z[TS][32], B[TS][NPT], C[TS][NPT]
+// WORK slot (two of them):  dlu[TS][32] float2 = (softplus(delta+bias), that * u),  ypart[NS][TS][32] fp32,
+//     and for bf16 I/O the fp32 copies Bf[TS][NPT], Cf[TS][NPT].
+template <typename T>
+struct FwdLayout {
+  int raw_u, raw_dl, raw_z, raw_B, raw_C, raw_bytes;
+  int w_dlu, w_y, w_Bf, w_Cf, work_bytes;
+  __host__ __device__ FwdLayout(int NS, int NPT) {
+    int o = 0;
+    raw_u = o, o += kTS * kDT * (int)sizeof(T);
+    raw_dl = o, o += kTS * kDT * (int)sizeof(T);
+    raw_z = o, o += kTS * kDT * (int)sizeof(T);
+    raw_B = o, o += kTS * NPT * (int)sizeof(T);
+    raw_C = o, o += kTS * NPT * (int)sizeof(T);
+    raw_bytes = (o + 127) & ~127;
+    o = 0;
+    w_dlu = o, o += kTS * kDT * 8;
+    w_y = o, o += NS * kTS * kDT * 4;
+    w_Bf = o, o += (sizeof(T) == 4 ? 0 : kTS * NPT * 4);
+    w_Cf = o, o += (sizeof(T) == 4 ? 0 : kTS * NPT * 4);
+    work_bytes = (o + 127) & ~127;
+  }
+};
+
+template <typename T, int NPER, int RR>
+__global__ void __launch_bounds__((kMaxScanWarps + kHelperWarps) * 32) scan_fwd_kernel(const ScanFwdParams p) {
+  static_assert(NPER % 4 == 0, "states per thread come in float4 groups");
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int NS = p.NS, NPT = p.NPT;
+  const int b = blockIdx.y, d0 = blockIdx.x * kDT;
+  const FwdLayout<T> lay(NS, NPT);
+  unsigned char* const raw_base = smem;
+  unsigned char* const work_base = smem + (size_t)RR * lay.raw_bytes;
+  const int nst = (p.L + kTS - 1) / kTS;
+  const int nscan_threads = NS * 32;
+  const int bar_count = nscan_threads + kHelperThreads;
+  // barrier ids: 1,2 = READY[work slot]; 3,4 = DONE[work slot]; 5 = helpers only
+
+  if (warp < NS) {
+    // ======================================= SCAN WARPS ===============================================
+    const int s = warp, d = d0 + lane;
+    float2 A2[NPER / 2], h[NPER / 2];
+#pragma unroll
+    for (int j = 0; j < NPER; ++j) {
+      const int n = s * NPER + j;
+      const bool ok = (d < p.D) && (n < p.N);
+      const float a = ok ? p.A[(int64_t)d * p.N + n] * kLog2e : 0.f;
+      const float h0 = (ok && p.h_init) ? p.h_init[((int64_t)b * p.D + d) * p.N + n] : 0.f;
+      if (j & 1) A2[j / 2].y = a, h[j / 2].y = h0;
+      else A2[j / 2].x = a, h[j / 2].x = h0;
+    }
+    int rslot = 0;
+    for (int c = 0; c < nst; ++c) {
+      const int ws = c & 1;
+      unsigned char* wbase = work_base + (size_t)ws * lay.work_bytes;
+      unsigned char* rbase = raw_base + (size_t)rslot * lay.raw_bytes;
+      const float2* dlu = reinterpret_cast<const float2*>(wbase + lay.w_dlu) + lane;
+      const float* Bf = (sizeof(T) == 4 ? reinterpret_cast<const float*>(rbase + lay.raw_B)
+                                        : reinterpret_cast<const float*>(wbase + lay.w_Bf)) + s * NPER;
+      const float* Cf = (sizeof(T) == 4 ? reinterpret_cast<const float*>(rbase + lay.raw_C)
+                                        : reinterpret_cast<const float*>(wbase + lay.w_Cf)) + s * NPER;
+      float* yp = reinterpret_cast<float*>(wbase + lay.w_y) + (s * kTS) * kDT + lane;
+      bar_sync(1 + ws, bar_count);  // stage c prepared
+      // Operands of timestep t+1 are fetched BEFORE timestep t is computed and stored: ptxas will not move a
+      // shared load above an earlier shared store it cannot disambiguate.
+      float2 dd_cur, dd_nxt;
+      float4 Bc[NPER / 4], Cc[NPER / 4], Bn[NPER / 4], Cn[NPER / 4];
+      auto fetch = [&](int t, float2& dd, float4 (&Bv)[NPER / 4], float4 (&Cv)[NPER / 4]) {
+        dd = dlu[t * kDT];
+#pragma unroll
+        for (int q = 0; q < NPER / 4; ++q) {
+          Bv[q] = *reinterpret_cast<const float4*>(Bf + t * NPT + 4 * q);
+          Cv[q] = *reinterpret_cast<const float4*>(Cf + t * NPT + 4 * q);
+        }
+      };
+      fetch(0, dd_cur, Bc, Cc);
+#pragma unroll
+      for (int t = 0; t < kTS; ++t) {
+        if (t + 1 < kTS) fetch(t + 1, dd_nxt, Bn, Cn);
+        const float2 dl2 = make_float2(dd_cur.x, dd_cur.x), du2 = make_float2(dd_cur.y, dd_cur.y);
+        float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int q = 0; q < NPER / 4; ++q) {
+          const float2 B01 = make_float2(Bc[q].x, Bc[q].y), B23 = make_float2(Bc[q].z, Bc[q].w);
+          const float2 C01 = make_float2(Cc[q].x, Cc[q].y), C23 = make_float2(Cc[q].z, Cc[q].w);
+          const float2 g0 = __fmul2_rn(dl2, A2[2 * q]), g1 = __fmul2_rn(dl2, A2[2 * q + 1]);
+          const float2 a0 = make_float2(ex2_approx(g0.x), ex2_approx(g0.y));
+          const float2 a1 = make_float2(ex2_approx(g1.x), ex2_approx(g1.y));
+          h[2 * q] = __ffma2_rn(a0, h[2 * q], __fmul2_rn(du2, B01));
+          h[2 * q + 1] = __ffma2_rn(a1, h[2 * q + 1], __fmul2_rn(du2, B23));
+          acc = __ffma2_rn(h[2 * q], C01, acc);
+          acc = __ffma2_rn(h[2 * q + 1], C23, acc);
+        }
+        sts_f32(yp + t * kDT, acc.x + acc.y);
+        dd_cur = dd_nxt;
+#pragma unroll
+        for (int q = 0; q < NPER / 4; ++q) Bc[q] = Bn[q], Cc[q] = Cn[q];
+      }
+      // h is now the state at the start of checkpoint chunk c + 1
+      if (p.ckpt != nullptr && (c + 1) * kTS < p.L && d < p.D) {
+        float* ck = p.ckpt + (((int64_t)b * p.nck + (c + 1)) * p.N + s * NPER) * p.D + d;
+#pragma unroll
+        for (int j = 0; j < NPER; ++j)
+          if (s * NPER + j < p.N) ck[(int64_t)j * p.D] = (j & 1) ? h[j / 2].y : h[j / 2].x;
+      }
+      bar_arrive(3 + ws, bar_count);  // stage c scanned
+      rslot = (rslot + 1 == RR) ? 0 : rslot + 1;
+    }
+    if (p.h_last != nullptr && d < p.D) {
+#pragma unroll
+      for (int j = 0; j < NPER; ++j) {
+        const int n = s * NPER + j;
+        if (n < p.N) p.h_last[((int64_t)b * p.D + d) * p.N + n] = (j & 1) ? h[j / 2].y : h[j / 2].x;
+      }
+    }
+    return;
+  }
+
+  // ========================================= HELPER WARPS ===============================================
+  const int ht = tid - nscan_threads;  // 0..127
   const int dvalid = min(kDT, p.D - d0);
-  const int NPT = p.NPT, NS = p.NS;
   const bool has_z = p.flags & MAMBA_FLAG_HAS_Z;
-
-  // ---- carve shared memory ---------------------------------------------------------------
-  const int raw_stage_elems = 3 * kLCS * kDT + 2 * kLCS * NPT;
-  T* raw = reinterpret_cast<T*>(smem_raw);
-  size_t raw_bytes = (size_t)2 * raw_stage_elems * sizeof(T);
-  raw_bytes = (raw_bytes + 15) & ~(size_t)15;
-  float* wdl = reinterpret_cast<float*>(smem_raw + raw_bytes);
-  float* wdu = wdl + kLCS * kDT;
-  float* wB = wdu + kLCS * kDT;
-  float* wC = wB + kLCS * NPT;
-  float* ypart = wC + kLCS * NPT;  // [NS][kLCS][kDT]
-
-  auto stage = [&](int st) {
-    FwdSmem<T> r;
-    T* base = raw + (size_t)st * raw_stage_elems;
-    r.u = base;
-    r.dl = r.u + kLCS * kDT;
-    r.z = r.dl + kLCS * kDT;
-    r.Bm = r.z + kLCS * kDT;
-    r.Cm = r.Bm + kLCS * NPT;
-    return r;
-  };
+  const bool do_softplus = p.flags & MAMBA_FLAG_DELTA_SOFTPLUS;
+  // this thread's element of every stage: timestep ht >> 3, channels 4*(ht & 7) .. +3
+  const int my_t = ht >> 3, my_c = 4 * (ht & 7);
+  float bias4[4], D4[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int d = d0 + my_c + e;
+    bias4[e] = ((p.flags & MAMBA_FLAG_HAS_DELTA_BIAS) && d < p.D) ? p.dbias[d] : 0.f;
+    D4[e] = ((p.flags & MAMBA_FLAG_HAS_D) && d < p.D) ? p.Dv[d] : 0.f;
+  }
 
   const T* gu = static_cast<const T*>(p.u) + (int64_t)b * p.u_bs + d0;
   const T* gdl = static_cast<const T*>(p.delta) + (int64_t)b * p.delta_bs + d0;
@@ -81,167 +241,209 @@ __global__ void __launch_bounds__(kMaxWarps * 32) scan_fwd_kernel(const ScanFwdP
   const T* gC = static_cast<const T*>(p.Cm) + (int64_t)b * p.C_bs;
   T* gout = static_cast<T*>(p.out) + (int64_t)b * p.out_bs + d0;
 
-  auto issue_loads = [&](int st, int c) {
-    FwdSmem<T> r = stage(st);
-    const int t0 = c * kLCS;
-    const int rows_valid = min(kLCS, p.L - t0);
-    load_tile_async<T>(r.u, kDT, gu + (int64_t)t0 * p.u_ls, p.u_ls, kLCS, rows_valid, dvalid, p.vec_u, tid, nthreads);
-    load_tile_async<T>(r.dl, kDT, gdl + (int64_t)t0 * p.delta_ls, p.delta_ls, kLCS, rows_valid, dvalid, p.vec_delta,
-                       tid, nthreads);
-    if (has_z)
-      load_tile_async<T>(r.z, kDT, gz + (int64_t)t0 * p.z_ls, p.z_ls, kLCS, rows_valid, dvalid, p.vec_z, tid,
-                         nthreads);
-    load_tile_async<T>(r.Bm, NPT, gB + (int64_t)t0 * p.B_ls, p.B_ls, kLCS, rows_valid, p.N, p.vec_B, tid, nthreads);
-    load_tile_async<T>(r.Cm, NPT, gC + (int64_t)t0 * p.C_ls, p.C_ls, kLCS, rows_valid, p.N, p.vec_C, tid, nthreads);
+  // ---- fast load path: full 32-channel tile, 16-byte aligned everything: one precomputed cp.async per tile ----
+  constexpr int VEC = 16 / (int)sizeof(T);         // elements per 16-byte vector
+  constexpr int VPR = kDT / VEC;                    // vectors per activation row (8 fp32 / 4 bf16)
+  const bool fast = p.vec_u && p.vec_delta && (!has_z || p.vec_z) && p.vec_B && p.vec_C && dvalid == kDT;
+  const bool act_mine = ht < kTS * VPR;             // this thread owns one vector of each activation tile
+  const int a_row = ht / VPR, a_col = (ht % VPR) * VEC;
+  const int bc_vpr = NPT / VEC;                     // vectors per B/C row (NPT is a multiple of 8)
+  const int bc_nvec = kTS * bc_vpr;
+  int bc_row[kMaxBCVec], bc_col[kMaxBCVec];
+#pragma unroll
+  for (int k = 0; k < kMaxBCVec; ++k) {
+    const int i = ht + k * kHelperThreads;
+    bc_row[k] = i / bc_vpr;
+    bc_col[k] = (i - bc_row[k] * bc_vpr) * VEC;
+  }
+  const bool bc_fast = fast && bc_nvec <= kMaxBCVec * kHelperThreads;
+
+  auto zero16 = [](void* dst) { *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u); };
+
+  auto issue_loads = [&](int c, int rslot) {
+    if (c < nst) {
+      unsigned char* base = raw_base + (size_t)rslot * lay.raw_bytes;
+      const int t0 = c * kTS;
+      const int rv = min(kTS, p.L - t0);
+      T* su = reinterpret_cast<T*>(base + lay.raw_u);
+      T* sdl = reinterpret_cast<T*>(base + lay.raw_dl);
+      T* sz = reinterpret_cast<T*>(base + lay.raw_z);
+      T* sB = reinterpret_cast<T*>(base + lay.raw_B);
+      T* sC = reinterpret_cast<T*>(base + lay.raw_C);
+      if (fast) {
+        if (act_mine) {
+          const int so = a_row * kDT + a_col;
+          if (a_row < rv) {
+            const int64_t t = t0 + a_row;
+            cp_async16(su + so, gu + t * p.u_ls + a_col);
+            cp_async16(sdl + so, gdl + t * p.delta_ls + a_col);
+            if (has_z) cp_async16(sz + so, gz + t * p.z_ls + a_col);
+          } else {
+            zero16(su + so), zero16(sdl + so);
+            if (has_z) zero16(sz + so);
+          }
+        }
+      } else {
+        load_tile_async<T>(su, kDT, gu + (int64_t)t0 * p.u_ls, p.u_ls, kTS, rv, dvalid, p.vec_u, ht, kHelperThreads);
+        load_tile_async<T>(sdl, kDT, gdl + (int64_t)t0 * p.delta_ls, p.delta_ls, kTS, rv, dvalid, p.vec_delta, ht,
+                           kHelperThreads);
+        if (has_z)
+          load_tile_async<T>(sz, kDT, gz + (int64_t)t0 * p.z_ls, p.z_ls, kTS, rv, dvalid, p.vec_z, ht, kHelperThreads);
+      }
+      if (bc_fast) {
+#pragma unroll
+        for (int k = 0; k < kMaxBCVec; ++k) {
+          if (ht + k * kHelperThreads < bc_nvec) {
+            const int so = bc_row[k] * NPT + bc_col[k];
+            if (bc_row[k] < rv && bc_col[k] + VEC <= p.N) {
+              const int64_t t = t0 + bc_row[k];
+              cp_async16(sB + so, gB + t * p.B_ls + bc_col[k]);
+              cp_async16(sC + so, gC + t * p.C_ls + bc_col[k]);
+            } else if (bc_row[k] < rv && bc_col[k] < p.N) {  // vector straddles N: guarded scalars
+              const int64_t t = t0 + bc_row[k];
+              for (int e = 0; e < VEC; ++e) {
+                const bool ok = bc_col[k] + e < p.N;
+                sB[so + e] = ok ? gB[t * p.B_ls + bc_col[k] + e] : T(0.f);
+                sC[so + e] = ok ? gC[t * p.C_ls + bc_col[k] + e] : T(0.f);
+              }
+            } else {
+              zero16(sB + so), zero16(sC + so);
+            }
+          }
+        }
+      } else {
+        load_tile_async<T>(sB, NPT, gB + (int64_t)t0 * p.B_ls, p.B_ls, kTS, rv, p.N, p.vec_B, ht, kHelperThreads);
+        load_tile_async<T>(sC, NPT, gC + (int64_t)t0 * p.C_ls, p.C_ls, kTS, rv, p.N, p.vec_C, ht, kHelperThreads);
+      }
+    }
+    cp_async_commit();  // always commit so that the group arithmetic below is uniform
   };
 
-  // ---- per-thread constants and state ----------------------------------------------------
-  float A2[NPER], h[NPER];
+  auto pre_pass = [&](int c, int rslot) {
+    unsigned char* rbase = raw_base + (size_t)rslot * lay.raw_bytes;
+    unsigned char* wbase = work_base + (size_t)(c & 1) * lay.work_bytes;
+    const int rv = min(kTS, p.L - c * kTS);
+    float dl[4], uu[4];
+    V4<T>::ld(reinterpret_cast<const T*>(rbase + lay.raw_dl) + my_t * kDT + my_c, dl);
+    V4<T>::ld(reinterpret_cast<const T*>(rbase + lay.raw_u) + my_t * kDT + my_c, uu);
+    float r[8];
 #pragma unroll
-  for (int j = 0; j < NPER; ++j) {
-    const int n = s * NPER + j;
-    const bool ok = (d < p.D) && (n < p.N);
-    A2[j] = ok ? p.A[(int64_t)d * p.N + n] * kLog2e : 0.f;
-    h[j] = (ok && p.h_init) ? p.h_init[((int64_t)b * p.D + d) * p.N + n] : 0.f;
-  }
-  const float bias_d = ((p.flags & MAMBA_FLAG_HAS_DELTA_BIAS) && d < p.D) ? p.dbias[d] : 0.f;
-  const float D_d = ((p.flags & MAMBA_FLAG_HAS_D) && d < p.D) ? p.Dv[d] : 0.f;
-  const bool do_softplus = p.flags & MAMBA_FLAG_DELTA_SOFTPLUS;
+    for (int e = 0; e < 4; ++e) {
+      float v = dl[e] + bias4[e];
+      if (do_softplus) v = softplus_fast(v);
+      if (my_t >= rv) v = 0.f;  // padded timestep: a = 1, input 0 -> state unchanged
+      r[2 * e] = v, r[2 * e + 1] = v * uu[e];
+    }
+    float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float2*>(wbase + lay.w_dlu) + my_t * kDT + my_c);
+    dst[0] = make_float4(r[0], r[1], r[2], r[3]);
+    dst[1] = make_float4(r[4], r[5], r[6], r[7]);
+    if (sizeof(T) != 4) {
+      const T* sB = reinterpret_cast<const T*>(rbase + lay.raw_B);
+      const T* sC = reinterpret_cast<const T*>(rbase + lay.raw_C);
+      float* Bf = reinterpret_cast<float*>(wbase + lay.w_Bf);
+      float* Cf = reinterpret_cast<float*>(wbase + lay.w_Cf);
+      for (int i = ht; i < kTS * NPT; i += kHelperThreads) {
+        Bf[i] = IO<T>::cvt(sB[i]);
+        Cf[i] = IO<T>::cvt(sC[i]);
+      }
+    }
+  };
 
-  const int nst = (p.L + kLCS - 1) / kLCS;
-  issue_loads(0, 0);
-  cp_async_commit();
+  auto post_pass = [&](int c, int rslot) {
+    unsigned char* rbase = raw_base + (size_t)rslot * lay.raw_bytes;
+    unsigned char* wbase = work_base + (size_t)(c & 1) * lay.work_bytes;
+    const int t0 = c * kTS;
+    if (t0 + my_t >= p.L) return;
+    const float* yp = reinterpret_cast<const float*>(wbase + lay.w_y) + my_t * kDT + my_c;
+    float2 s01 = make_float2(0.f, 0.f), s23 = make_float2(0.f, 0.f);
+    for (int w = 0; w < NS; ++w) {
+      const float4 v = *reinterpret_cast<const float4*>(yp + w * kTS * kDT);
+      s01 = __fadd2_rn(s01, make_float2(v.x, v.y));
+      s23 = __fadd2_rn(s23, make_float2(v.z, v.w));
+    }
+    float y[4] = {s01.x, s01.y, s23.x, s23.y};
+    float uu[4];
+    V4<T>::ld(reinterpret_cast<const T*>(rbase + lay.raw_u) + my_t * kDT + my_c, uu);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) y[e] = fmaf(D4[e], uu[e], y[e]);
+    if (has_z) {
+      float zz[4];
+      V4<T>::ld(reinterpret_cast<const T*>(rbase + lay.raw_z) + my_t * kDT + my_c, zz);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) y[e] *= silu_fast(zz[e]);
+    }
+    T* o = gout + (int64_t)(t0 + my_t) * p.out_ls + my_c;
+    if (p.vec_out && my_c + 4 <= dvalid) {
+      V4<T>::st_global(o, y);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (my_c + e < dvalid) IO<T>::st(o + e, y[e]);
+    }
+  };
 
+  // prologue: RR - 1 stages in flight
+  for (int c = 0; c < RR - 1; ++c) issue_loads(c, c);
+  int rslot = 0;                 // raw slot of stage c
+  int pslot = RR - 1;            // raw slot of stage c - 1 (the one that is refilled at the end of iteration c)
   for (int c = 0; c < nst; ++c) {
-    if (c + 1 < nst) issue_loads((c + 1) & 1, c + 1);
-    cp_async_commit();
-    cp_async_wait<1>();
-    __syncthreads();
-
-    FwdSmem<T> r = stage(c & 1);
-    const int t0 = c * kLCS;
-    const int rows_valid = min(kLCS, p.L - t0);
-
-    // ---- pre-pass: discretisation inputs, once per (t, d) ---------------------------------
-    for (int i = tid; i < kLCS * kDT; i += nthreads) {  // i % 32 == lane
-      const int t = i >> 5;
-      float dl = 0.f, du = 0.f;
-      if (t < rows_valid) {
-        dl = IO<T>::cvt(r.dl[i]) + bias_d;
-        if (do_softplus) dl = softplus_f(dl);
-        du = dl * IO<T>::cvt(r.u[i]);
-      }
-      wdl[i] = dl;
-      wdu[i] = du;
+    cp_async_wait<RR - 2>();       // this thread's loads of stage c have landed
+    bar_sync(5, kHelperThreads);   // ... and every helper's (also: every helper is past post_pass(c - 2))
+    pre_pass(c, rslot);
+    bar_arrive(1 + (c & 1), bar_count);  // READY[work slot]
+    if (c >= 1) {
+      bar_sync(3 + ((c - 1) & 1), bar_count);  // DONE[work slot of c - 1]
+      post_pass(c - 1, pslot);
     }
-    for (int i = tid; i < kLCS * NPT; i += nthreads) {
-      wB[i] = IO<T>::cvt(r.Bm[i]);
-      wC[i] = IO<T>::cvt(r.Cm[i]);
-    }
-    __syncthreads();
-
-    // ---- main loop: the recurrence, h in registers ----------------------------------------
-#pragma unroll 1
-    for (int tc = 0; tc < kLCS; tc += CK) {
-      if (tc >= rows_valid) break;
-#pragma unroll 4
-      for (int tt = 0; tt < CK; ++tt) {
-        const int t = tc + tt;
-        const float dl = wdl[t * kDT + lane];
-        const float du = wdu[t * kDT + lane];
-        float Bv[NPER], Cv[NPER];
-        const float4* b4 = reinterpret_cast<const float4*>(wB + t * NPT + s * NPER);
-        const float4* c4 = reinterpret_cast<const float4*>(wC + t * NPT + s * NPER);
-#pragma unroll
-        for (int q = 0; q < NPER / 4; ++q) {
-          float4 bb = b4[q], cc = c4[q];
-          Bv[4 * q] = bb.x, Bv[4 * q + 1] = bb.y, Bv[4 * q + 2] = bb.z, Bv[4 * q + 3] = bb.w;
-          Cv[4 * q] = cc.x, Cv[4 * q + 1] = cc.y, Cv[4 * q + 2] = cc.z, Cv[4 * q + 3] = cc.w;
-        }
-        float acc = 0.f;
-#pragma unroll
-        for (int j = 0; j < NPER; ++j) {
-          const float a = ex2_approx(dl * A2[j]);
-          h[j] = fmaf(a, h[j], du * Bv[j]);
-          acc = fmaf(h[j], Cv[j], acc);
-        }
-        ypart[(s * kLCS + t) * kDT + lane] = acc;
-      }
-      const int tg_next = t0 + tc + CK;  // h now = state at the start of checkpoint chunk tg_next / CK
-      if (p.ckpt != nullptr && tg_next < p.L && d < p.D) {
-        float* ck = p.ckpt + (((int64_t)b * p.nck + tg_next / CK) * p.N) * p.D + d;
-#pragma unroll
-        for (int j = 0; j < NPER; ++j) {
-          const int n = s * NPER + j;
-          if (n < p.N) ck[(int64_t)n * p.D] = h[j];
-        }
-      }
-    }
-    __syncthreads();
-
-    // ---- post-pass: reduce over state slices, D skip, z gate, coalesced store --------------
-    for (int i = tid; i < kLCS * kDT; i += nthreads) {  // i % 32 == lane
-      const int t = i >> 5;
-      if (t < rows_valid && d < p.D) {
-        float y = 0.f;
-        for (int w = 0; w < NS; ++w) y += ypart[w * kLCS * kDT + i];
-        y = fmaf(D_d, IO<T>::cvt(r.u[i]), y);
-        if (has_z) y *= silu_f(IO<T>::cvt(r.z[i]));
-        IO<T>::st(gout + (int64_t)(t0 + t) * p.out_ls + lane, y);
-      }
-    }
-    __syncthreads();
+    bar_sync(5, kHelperThreads);   // every helper has finished reading stage c-1's raw tiles
+    issue_loads(c + RR - 1, pslot);
+    pslot = rslot;
+    rslot = (rslot + 1 == RR) ? 0 : rslot + 1;
   }
-
-  if (p.h_last != nullptr && d < p.D) {
-#pragma unroll
-    for (int j = 0; j < NPER; ++j) {
-      const int n = s * NPER + j;
-      if (n < p.N) p.h_last[((int64_t)b * p.D + d) * p.N + n] = h[j];
-    }
-  }
+  bar_sync(3 + ((nst - 1) & 1), bar_count);
+  post_pass(nst - 1, pslot);
 }
 
-static size_t fwd_smem_bytes(size_t elt, int NS, int NPT) {
-  size_t raw = (size_t)2 * (3 * kLCS * kDT + 2 * kLCS * NPT) * elt;
-  raw = (raw + 15) & ~(size_t)15;
-  size_t work = (size_t)4 * (2 * kLCS * kDT + 2 * kLCS * NPT + (size_t)NS * kLCS * kDT);
-  return raw + work;
+template <typename T>
+static size_t fwd_smem_bytes(int NS, int NPT, int RR) {
+  const FwdLayout<T> lay(NS, NPT);
+  return (size_t)RR * lay.raw_bytes + (size_t)2 * lay.work_bytes;
 }
 
-template <typename T, int NPER, int CK>
+template <typename T, int NPER, int RR>
 static int launch_fwd(const ScanFwdParams& p, cudaStream_t stream) {
-  const size_t smem = fwd_smem_bytes(sizeof(T), p.NS, p.NPT);
+  const size_t smem = fwd_smem_bytes<T>(p.NS, p.NPT, RR);
   if (smem > 227 * 1024) return set_error(MAMBA_ESIZE, "scan_fwd: d_state %d needs %zu B of shared memory", p.N, smem);
-  auto kern = scan_fwd_kernel<T, NPER, CK>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return set_error(MAMBA_ELAUNCH, "scan_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  auto kern = scan_fwd_kernel<T, NPER, RR>;
+  static thread_local size_t configured = 0;  // per instantiation: raise the dynamic-smem limit once per size
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_error(MAMBA_ELAUNCH, "scan_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    configured = smem;
+  }
   dim3 grid(ceil_div(p.D, kDT), p.B);
-  kern<<<grid, p.NS * 32, smem, stream>>>(p);
+  kern<<<grid, (p.NS + kHelperWarps) * 32, smem, stream>>>(p);
   count_launch();
   return check_launch("scan_fwd");
 }
 
 template <typename T, int NPER>
-static int dispatch_ck(const ScanFwdParams& p, int chunk, cudaStream_t stream) {
-  switch (chunk) {
-    case 8: return launch_fwd<T, NPER, 8>(p, stream);
-    case 16: return launch_fwd<T, NPER, 16>(p, stream);
-    case 32: return launch_fwd<T, NPER, 32>(p, stream);
-  }
-  return set_error(MAMBA_EINVAL, "scan_fwd: chunk must be 8, 16 or 32 (got %d)", chunk);
+static int dispatch_ring(const ScanFwdParams& p, cudaStream_t stream) {
+  // deep ring when a stage is short (few states): bytes in flight must cover HBM latency with one CTA per SM
+  if (p.N <= 32 && fwd_smem_bytes<T>(p.NS, p.NPT, 8) <= 100 * 1024) return launch_fwd<T, NPER, 8>(p, stream);
+  return launch_fwd<T, NPER, 4>(p, stream);
 }
 
 template <typename T>
-static int dispatch_nper(ScanFwdParams& p, int nper, int chunk, cudaStream_t stream) {
+static int dispatch_nper(ScanFwdParams& p, int nper, cudaStream_t stream) {
   p.NS = ceil_div(p.N, nper);
   const int np = p.NS * nper;
   p.NPT = (np + 7) & ~7;
-  if (p.NS > kMaxWarps) return set_error(MAMBA_ESIZE, "scan_fwd: d_state %d too large for %d states/thread", p.N, nper);
+  if (p.NS > kMaxScanWarps) return set_error(MAMBA_ESIZE, "scan_fwd: d_state %d too large for %d states/thread", p.N, nper);
   switch (nper) {
-    case 4: return dispatch_ck<T, 4>(p, chunk, stream);
-    case 8: return dispatch_ck<T, 8>(p, chunk, stream);
-    case 16: return dispatch_ck<T, 16>(p, chunk, stream);
+    case 4: return dispatch_ring<T, 4>(p, stream);
+    case 8: return dispatch_ring<T, 8>(p, stream);
+    case 16: return dispatch_ring<T, 16>(p, stream);
   }
   return set_error(MAMBA_EINVAL, "scan_fwd: variant must be 0, 4, 8 or 16 (got %d)", nper);
 }
@@ -272,11 +474,12 @@ extern "C" int mamba_scan_fwd(const MambaScanFwdArgs* a, void* stream) {
   if ((a->flags & MAMBA_FLAG_HAS_DELTA_BIAS) && !a->delta_bias)
     return set_error(MAMBA_EINVAL, "scan_fwd: HAS_DELTA_BIAS but delta_bias == NULL");
   if (a->dtype != MAMBA_F32 && a->dtype != MAMBA_BF16) return set_error(MAMBA_EDTYPE, "scan_fwd: dtype %d", a->dtype);
+  if (a->ckpt && a->chunk != kTS)
+    return set_error(MAMBA_EINVAL, "scan_fwd: chunk must be %d (got %d)", kTS, a->chunk);
 
   ScanFwdParams p{};
   p.B = a->batch, p.L = a->seqlen, p.D = a->dim, p.N = a->dstate, p.flags = a->flags;
-  const int chunk = a->ckpt ? a->chunk : 16;
-  p.nck = ceil_div(p.L, chunk);
+  p.nck = ceil_div(p.L, kTS);
   p.u = a->u, p.delta = a->delta, p.Bm = a->B, p.Cm = a->C, p.z = a->z, p.out = a->out;
   p.u_bs = a->u_bs, p.u_ls = a->u_ls, p.delta_bs = a->delta_bs, p.delta_ls = a->delta_ls;
   p.B_bs = a->B_bs, p.B_ls = a->B_ls, p.C_bs = a->C_bs, p.C_ls = a->C_ls;
@@ -290,11 +493,11 @@ extern "C" int mamba_scan_fwd(const MambaScanFwdArgs* a, void* stream) {
   p.vec_z = a->z ? vec_ok(a->z, a->z_bs, a->z_ls, elt) : 0;
   p.vec_B = vec_ok(a->B, a->B_bs, a->B_ls, elt);
   p.vec_C = vec_ok(a->C, a->C_bs, a->C_ls, elt);
+  p.vec_out = vec_ok(a->out, a->out_bs, a->out_ls, elt);
 
   int nper = a->variant;
-  if (nper == 0) nper = p.N >= 64 ? 16 : (p.N >= 32 ? 8 : 4);
-  while (nper < 16 && ceil_div(p.N, nper) > kMaxWarps) nper *= 2;
+  if (nper == 0) nper = p.N >= 64 ? 8 : 4;
+  while (nper < 16 && ceil_div(p.N, nper) > kMaxScanWarps) nper *= 2;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  return a->dtype == MAMBA_F32 ? dispatch_nper<float>(p, nper, chunk, st)
-                               : dispatch_nper<__nv_bfloat16>(p, nper, chunk, st);
+  return a->dtype == MAMBA_F32 ? dispatch_nper<float>(p, nper, st) : dispatch_nper<__nv_bfloat16>(p, nper, st);
 }
