@@ -29,7 +29,7 @@ class ScanFwdArgs(C.Structure):
     _fields_ = ([("struct_size", i32), ("dtype", i32), ("batch", i32), ("seqlen", i32), ("dim", i32), ("dstate", i32),
                  ("chunk", i32), ("flags", i32), ("variant", i32), ("reserved", i32)]
                 + _t("u") + _t("delta") + [("A", fp)] + _t("B") + _t("C") + [("D", fp)] + _t("z")
-                + [("delta_bias", fp)] + _t("out") + [("ckpt", fp), ("h_last", fp), ("h_init", fp)])
+                + [("delta_bias", fp)] + _t("out") + [("ckpt", fp), ("h_last", fp), ("h_init", fp)] + _t("y_pre"))
 
 
 class ScanBwdArgs(C.Structure):
@@ -38,7 +38,8 @@ class ScanBwdArgs(C.Structure):
                 + _t("u") + _t("delta") + [("A", fp)] + _t("B") + _t("C") + [("D", fp)] + _t("z")
                 + [("delta_bias", fp)] + _t("dout") + [("ckpt", fp)]
                 + _t("du") + _t("ddelta") + _t("dz") + _t("dB") + _t("dC")
-                + [("dA", fp), ("dD", fp), ("ddelta_bias", fp), ("workspace", vp), ("workspace_bytes", sz)])
+                + [("dA", fp), ("dD", fp), ("ddelta_bias", fp), ("workspace", vp), ("workspace_bytes", sz)]
+                + _t("y_pre"))
 
 
 class ConvArgs(C.Structure):
@@ -100,8 +101,8 @@ def lib() -> C.CDLL:
     L.mamba_conv1d_bwd_workspace_bytes.argtypes = [C.c_int] * 4
     L.mamba_rmsnorm_bwd_workspace_bytes.restype = sz
     L.mamba_rmsnorm_bwd_workspace_bytes.argtypes = [C.c_int64, C.c_int]
-    if L.mamba_abi_version() != 1:
-        raise MambaLibError(f"ABI version mismatch: library {L.mamba_abi_version()} != binding 1")
+    if L.mamba_abi_version() != 2:
+        raise MambaLibError(f"ABI version mismatch: library {L.mamba_abi_version()} != binding 2")
     _lib = L
     return L
 

@@ -48,6 +48,67 @@ __device__ __forceinline__ float softplus_grad_f(float x) {
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
 __device__ __forceinline__ float silu_f(float x) { return x / (1.f + expf(-x)); }
 
+__device__ __forceinline__ void st_cs_f4(float* p, float4 v);
+
+// ---- fast transcendental helpers (MUFU ex2 / lg2 / rcp; relative error ~1e-7, far inside rtol 1e-4) ----------
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// softplus with torch's threshold (x > 20 -> x).  For x < -4 the series of log1p(e) avoids the cancellation
+// of forming 1 + e in fp32.
+__device__ __forceinline__ float softplus_fast(float x) {
+  const float e = ex2_approx(x * kLog2e);
+  const float series = e * fmaf(e, fmaf(e, fmaf(e, -0.25f, 0.33333334f), -0.5f), 1.f);
+  const float full = lg2_approx(1.f + e) * kLn2;
+  const float r = x < -4.f ? series : full;
+  return x > 20.f ? x : r;
+}
+__device__ __forceinline__ float silu_fast(float x) { return x * rcp_approx(1.f + ex2_approx(-x * kLog2e)); }
+
+// Shared-memory store issued through asm so that nvvm does not order later shared loads behind it.
+__device__ __forceinline__ void sts_f32(float* p, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "f"(v));
+}
+__device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int count) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+// 4 consecutive elements of T <-> 4 floats (128-bit / 64-bit accesses)
+template <typename T>
+struct V4;
+template <>
+struct V4<float> {
+  static __device__ __forceinline__ void ld(const float* p, float (&v)[4]) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w;
+  }
+  static __device__ __forceinline__ void st_global(float* p, const float (&v)[4]) { st_cs_f4(p, make_float4(v[0], v[1], v[2], v[3])); }
+};
+template <>
+struct V4<__nv_bfloat16> {
+  static __device__ __forceinline__ void ld(const __nv_bfloat16* p, float (&v)[4]) {
+    const uint2 t = *reinterpret_cast<const uint2*>(p);
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&t.x);
+    const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&t.y);
+    v[0] = __low2float(a), v[1] = __high2float(a), v[2] = __low2float(b), v[3] = __high2float(b);
+  }
+  static __device__ __forceinline__ void st_global(__nv_bfloat16* p, const float (&v)[4]) {
+    const __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+    uint2 t;
+    t.x = *reinterpret_cast<const uint32_t*>(&a), t.y = *reinterpret_cast<const uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = t;
+  }
+};
+
+
 // ---- async copies (LDGSTS) ----------------------------------------------------------------
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
   uint32_t s = (uint32_t)__cvta_generic_to_shared(smem_dst);

@@ -1,34 +1,42 @@
-// scan_bwd.cu — fused selective-scan backward for sm_100a.
+// scan_bwd.cu — fused selective-scan backward for sm_100a (warp-specialised).
 //
 // The reference has no explicit backward: torch autograd differentiates the python loop of
 // MambaBlock.selective_scan (models/mamba/__pycache__/simple_mamba.cpython-311.pyc @L310-333), saving the
-// [B, L, D, N] tensors deltaA / deltaB_u and every per-step state.  Here the forward is recomputed
-// chunk by chunk from the checkpoints written by scan_fwd and the adjoint recurrence
+// [B, L, D, N] tensors deltaA / deltaB_u and every per-step state.  Here the forward is recomputed chunk by chunk
+// (16 timesteps) from the checkpoints written by scan_fwd and the adjoint recurrence
 //     dh_t = C_t * dy_t + a_{t+1} * dh_{t+1}
 // runs in registers; nothing of size B*L*D*N touches HBM.
 //
-// Mapping: one CTA owns (batch b, 32 channels).  Each thread owns a 4-channel x NPER-state register
-// tile; a warp is 8 channel-lanes x 4 state-lanes, warps tile the state axis.  Sums over states
-// (d_delta, d_u, y) are 2 butterfly steps across the state-lanes, sums over channels (dB, dC) are
-// 3 butterfly steps across the channel-lanes followed by a per-CTA partial that a finalize kernel
-// reduces over the D/32 CTAs of a batch in a fixed order (deterministic, no atomics).
-// Chunks are walked from the end of the sequence to the start; the inputs of chunk c-1 are prefetched
-// into shared memory with cp.async while chunk c is processed.  Per chunk:
-//   pre-pass  : softplus(delta+bias), delta*u, dy = dout*silu(z), fp32 copies of B and C
-//   recompute : h_t for the CK steps of the chunk from the checkpoint (kept in shared memory)
-//   reverse   : adjoint recurrence; per-step partials of d_delta, d_u, dB, dC
-//   post-pass : finish d_delta (softplus'), d_u (+D*dy), dz, accumulate dD and d_bias, store.
+// Per (b, t, d, n) the work is 2 MUFU.EX2 (a_t in the recompute and again in the reverse sweep — keeping a_t in
+// shared memory instead would saturate the shared-memory pipe) and 13 fp32 multiply-adds, i.e. the kernel is
+// paced by the MUFU pipe with the FMA pipe and the issue slots close behind; its HBM traffic is ~10x smaller
+// than that.  Organisation (same producer/consumer scheme as scan_fwd.cu):
+//   * one CTA owns (batch b, 32 channels); chunks are walked from the end of the sequence to the start.
+//   * SCAN warps: each thread owns a 4-channel x NPER-state register tile (a warp is 8 channel-lanes x 4
+//     state-lanes; warps tile the state axis).  Recompute: h_t for the 16 steps of the chunk -> shared memory
+//     (thread-private, conflict-free float4).  Reverse sweep: all arithmetic in packed fp32x2 (FFMA2/FMUL2) on
+//     channel pairs; a_t*h_{t-1} is obtained as h_t - delta*u*B so h_{t-1} is never re-read.  Sums over states
+//     (d_delta, d_u) are 2 butterfly steps across the state-lanes + one per-warp partial in shared memory, sums
+//     over channels (dB, dC) 3 butterfly steps across the channel-lanes.
+//   * HELPER warps (4): cp.async loads one chunk ahead, pre-pass (softplus(delta+bias), delta*u,
+//     dy = dout*silu(z)), post-pass (finish d_delta (softplus'), d_u (+D*dy), dz from the saved pre-gate output,
+//     accumulate dD / d_bias, 128-bit stores, per-CTA dB/dC partial -> workspace).
+//   * a finalize kernel reduces the per-CTA / per-batch partials in a fixed order (deterministic, no atomics).
 #include "common.cuh"
 
 namespace mb {
 
-constexpr int kBD = 32;       // channels per CTA
-constexpr int kBMaxWarps = 8; // state-warps per CTA
+constexpr int kBD = 32;        // channels per CTA
+constexpr int kCK = 16;        // timesteps per chunk (= checkpoint interval of scan_fwd)
+constexpr int kBHelperWarps = 4;
+constexpr int kBHelperThreads = kBHelperWarps * 32;
+constexpr int kBMaxWarps = 8;  // scan warps per CTA
+constexpr int kBRing = 2;      // raw-tile ring depth (a chunk is >= 2 us of work at d_state 64)
 
 struct ScanBwdParams {
   int B, L, D, N, NW, NPT, nck, flags, ntiles;
-  const void *u, *delta, *Bm, *Cm, *z, *dout;
-  int64_t u_bs, u_ls, delta_bs, delta_ls, B_bs, B_ls, C_bs, C_ls, z_bs, z_ls, dout_bs, dout_ls;
+  const void *u, *delta, *Bm, *Cm, *z, *dout, *ypre;
+  int64_t u_bs, u_ls, delta_bs, delta_ls, B_bs, B_ls, C_bs, C_ls, z_bs, z_ls, dout_bs, dout_ls, ypre_bs, ypre_ls;
   void *du, *ddelta, *dz, *dB, *dC;
   int64_t du_bs, du_ls, ddelta_bs, ddelta_ls, dz_bs, dz_ls, dB_bs, dB_ls, dC_bs, dC_ls;
   const float *A, *Dv, *dbias, *ckpt;
@@ -37,335 +45,465 @@ struct ScanBwdParams {
   float *ws_dB, *ws_dC;  // [B][ntiles][L][N]
   float *ws_dA;          // [B][N][D]
   float *ws_dD, *ws_db;  // [B][D]
-  int vec_u, vec_delta, vec_z, vec_dout, vec_B, vec_C, vec_ck;
+  int vec_u, vec_delta, vec_z, vec_dout, vec_ypre, vec_B, vec_C, vec_ck, vec_du, vec_ddelta, vec_dz;
 };
 
 template <int NPER>
 __device__ __forceinline__ void lds_vec(float (&dst)[NPER], const float* src) {
   if constexpr (NPER == 4) {
-    float4 v = *reinterpret_cast<const float4*>(src);
+    const float4 v = *reinterpret_cast<const float4*>(src);
     dst[0] = v.x, dst[1] = v.y, dst[2] = v.z, dst[3] = v.w;
   } else if constexpr (NPER == 2) {
-    float2 v = *reinterpret_cast<const float2*>(src);
+    const float2 v = *reinterpret_cast<const float2*>(src);
     dst[0] = v.x, dst[1] = v.y;
   } else {
 #pragma unroll
     for (int j = 0; j < NPER; ++j) dst[j] = src[j];
   }
 }
+template <int NPER>
+__device__ __forceinline__ void sts_vec(float* dst, const float (&v)[NPER]) {
+  if constexpr (NPER == 4) {
+    *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+  } else if constexpr (NPER == 2) {
+    *reinterpret_cast<float2*>(dst) = make_float2(v[0], v[1]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < NPER; ++j) dst[j] = v[j];
+  }
+}
+__device__ __forceinline__ float2 shfl_xor2(float2 v, int m) {
+  return make_float2(__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m));
+}
 
-template <typename T, int NPER, int CK>
-__global__ void __launch_bounds__(kBMaxWarps * 32, 1) scan_bwd_kernel(const ScanBwdParams p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const int nthreads = blockDim.x;
-  const int ld = lane & 7, ln = lane >> 3;
+// Shared-memory layout.
+//   RAW ring slot (cp.async targets, element type T): u, delta, z, dout, ypre [CK][32];  B, C [CK][NPT]
+//   WORK slot (two): wdl, wdu, wdy fp32 [CK][32];  (bf16 I/O only) Bf, Cf fp32 [CK][NPT];
+//                    pg, pS [NW][CK][32] (per-warp partial sums over states);  redB, redC [CK][NPT]
+//   hs: float4 [CK][NPER][scan threads]  (h_t of the chunk, 4 channels per float4, thread-private)
+template <typename T>
+struct BwdLayout {
+  int raw_u, raw_dl, raw_z, raw_do, raw_yp, raw_B, raw_C, raw_bytes;
+  int w_dl, w_du, w_dy, w_Bf, w_Cf, w_pg, w_pS, w_rB, w_rC, work_bytes;
+  int hs_bytes;
+  __host__ __device__ BwdLayout(int NW, int NPT, int NPER) {
+    int o = 0;
+    raw_u = o, o += kCK * kBD * (int)sizeof(T);
+    raw_dl = o, o += kCK * kBD * (int)sizeof(T);
+    raw_z = o, o += kCK * kBD * (int)sizeof(T);
+    raw_do = o, o += kCK * kBD * (int)sizeof(T);
+    raw_yp = o, o += kCK * kBD * (int)sizeof(T);
+    raw_B = o, o += kCK * NPT * (int)sizeof(T);
+    raw_C = o, o += kCK * NPT * (int)sizeof(T);
+    raw_bytes = (o + 127) & ~127;
+    o = 0;
+    w_dl = o, o += kCK * kBD * 4;
+    w_du = o, o += kCK * kBD * 4;
+    w_dy = o, o += kCK * kBD * 4;
+    w_Bf = o, o += (sizeof(T) == 4 ? 0 : kCK * NPT * 4);
+    w_Cf = o, o += (sizeof(T) == 4 ? 0 : kCK * NPT * 4);
+    w_pg = o, o += NW * kCK * kBD * 4;
+    w_pS = o, o += NW * kCK * kBD * 4;
+    w_rB = o, o += kCK * NPT * 4;
+    w_rC = o, o += kCK * NPT * 4;
+    work_bytes = (o + 127) & ~127;
+    hs_bytes = kCK * NPER * NW * 32 * 16;
+  }
+};
+
+template <typename T, int NPER, int NW>
+__global__ void __launch_bounds__((NW + kBHelperWarps) * 32, 1) scan_bwd_kernel(const ScanBwdParams p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NPT = ((NW * 4 * NPER + 7) / 8) * 8;  // padded d_state of the shared tiles
   const int b = blockIdx.y, tile = blockIdx.x;
   const int d0 = tile * kBD;
   const int dvalid = min(kBD, p.D - d0);
-  const int NPT = p.NPT, NW = p.NW;
+  const BwdLayout<T> lay(NW, NPT, NPER);
+  unsigned char* const raw_base = smem;
+  unsigned char* const work_base = smem + (size_t)kBRing * lay.raw_bytes;
+  float4* const hs = reinterpret_cast<float4*>(work_base + (size_t)2 * lay.work_bytes);
+  const int nck = p.nck;
+  constexpr int nscan_threads = NW * 32;
+  constexpr int bar_count = nscan_threads + kBHelperThreads;
   const bool has_z = p.flags & MAMBA_FLAG_HAS_Z;
+  // barrier ids: 1,2 = READY[work slot]; 3,4 = DONE[work slot]; 5 = helpers only.  Iteration i handles chunk nck-1-i.
+
+  if (warp < NW) {
+    // ========================================= SCAN WARPS ===============================================
+    const int ld = lane & 7, ln = lane >> 3;
+    const int nbase = (warp * 4 + ln) * NPER;  // first state of this thread
+    const int dl0 = 4 * ld;                    // first (tile-local) channel of this thread
+    float2 A2[2][NPER], dAacc[2][NPER], dhc[2][NPER];
+#pragma unroll
+    for (int j = 0; j < NPER; ++j) {
+      float a[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int d = d0 + dl0 + i, n = nbase + j;
+        a[i] = (d < p.D && n < p.N) ? p.A[(int64_t)d * p.N + n] * kLog2e : 0.f;
+      }
+      A2[0][j] = make_float2(a[0], a[1]), A2[1][j] = make_float2(a[2], a[3]);
+      dAacc[0][j] = dAacc[1][j] = make_float2(0.f, 0.f);
+      dhc[0][j] = dhc[1][j] = make_float2(0.f, 0.f);
+    }
+    // chunk-start state of chunk c from the forward's checkpoints (zero for chunk 0)
+    auto load_ckpt = [&](int c, float2 (&h)[2][NPER]) {
+#pragma unroll
+      for (int j = 0; j < NPER; ++j) {
+        const int n = nbase + j;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c > 0 && n < p.N) {
+          const float* ck = p.ckpt + (((int64_t)b * nck + c) * p.N + n) * p.D + d0 + dl0;
+          if (p.vec_ck && dl0 + 4 <= dvalid) {
+            v = __ldg(reinterpret_cast<const float4*>(ck));
+          } else {
+            if (dl0 + 0 < dvalid) v.x = ck[0];
+            if (dl0 + 1 < dvalid) v.y = ck[1];
+            if (dl0 + 2 < dvalid) v.z = ck[2];
+            if (dl0 + 3 < dvalid) v.w = ck[3];
+          }
+        }
+        h[0][j] = make_float2(v.x, v.y), h[1][j] = make_float2(v.z, v.w);
+      }
+    };
+    float2 hnext[2][NPER];
+    load_ckpt(nck - 1, hnext);
+    float4* const hst = hs + tid;  // + (t * NPER + j) * nscan_threads
+
+    int rslot = 0;
+    for (int it = 0; it < nck; ++it) {
+      const int c = nck - 1 - it;
+      const int ws = it & 1;
+      unsigned char* wbase = work_base + (size_t)ws * lay.work_bytes;
+      unsigned char* rbase = raw_base + (size_t)rslot * lay.raw_bytes;
+      const float* wdl = reinterpret_cast<const float*>(wbase + lay.w_dl) + dl0;
+      const float* wdu = reinterpret_cast<const float*>(wbase + lay.w_du) + dl0;
+      const float* wdy = reinterpret_cast<const float*>(wbase + lay.w_dy) + dl0;
+      const float* Bf = (sizeof(T) == 4 ? reinterpret_cast<const float*>(rbase + lay.raw_B)
+                                        : reinterpret_cast<const float*>(wbase + lay.w_Bf)) + nbase;
+      const float* Cf = (sizeof(T) == 4 ? reinterpret_cast<const float*>(rbase + lay.raw_C)
+                                        : reinterpret_cast<const float*>(wbase + lay.w_Cf)) + nbase;
+      float* pg = reinterpret_cast<float*>(wbase + lay.w_pg) + (warp * kCK) * kBD + dl0;
+      float* pS = reinterpret_cast<float*>(wbase + lay.w_pS) + (warp * kCK) * kBD + dl0;
+      float* redB = reinterpret_cast<float*>(wbase + lay.w_rB) + nbase;
+      float* redC = reinterpret_cast<float*>(wbase + lay.w_rC) + nbase;
+
+      float2 h[2][NPER];
+#pragma unroll
+      for (int j = 0; j < NPER; ++j) h[0][j] = hnext[0][j], h[1][j] = hnext[1][j];
+      bar_sync(1 + ws, bar_count);  // chunk c prepared
+
+      // ---- forward recompute: h_t for every step of the chunk -> shared memory ---------------------------
+#pragma unroll 4
+      for (int t = 0; t < kCK; ++t) {
+        const float4 dl4 = *reinterpret_cast<const float4*>(wdl + t * kBD);
+        const float4 du4 = *reinterpret_cast<const float4*>(wdu + t * kBD);
+        const float2 dlp[2] = {make_float2(dl4.x, dl4.y), make_float2(dl4.z, dl4.w)};
+        const float2 dup[2] = {make_float2(du4.x, du4.y), make_float2(du4.z, du4.w)};
+        float Bv[NPER];
+        lds_vec<NPER>(Bv, Bf + t * NPT);
+#pragma unroll
+        for (int j = 0; j < NPER; ++j) {
+          const float2 Bb = make_float2(Bv[j], Bv[j]);
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const float2 g = __fmul2_rn(dlp[q], A2[q][j]);
+            const float2 a = make_float2(ex2_approx(g.x), ex2_approx(g.y));
+            h[q][j] = __ffma2_rn(a, h[q][j], __fmul2_rn(dup[q], Bb));
+          }
+          hst[(t * NPER + j) * nscan_threads] = make_float4(h[0][j].x, h[0][j].y, h[1][j].x, h[1][j].y);
+        }
+      }
+      // prefetch the next chunk's start state: its latency hides behind the reverse sweep
+      if (c > 0) load_ckpt(c - 1, hnext);
+
+      // ---- reverse sweep: adjoint recurrence ------------------------------------------------------------------
+#pragma unroll 2
+      for (int t = kCK - 1; t >= 0; --t) {
+        const float4 dl4 = *reinterpret_cast<const float4*>(wdl + t * kBD);
+        const float4 du4 = *reinterpret_cast<const float4*>(wdu + t * kBD);
+        const float4 dy4 = *reinterpret_cast<const float4*>(wdy + t * kBD);
+        const float2 dlp[2] = {make_float2(dl4.x, dl4.y), make_float2(dl4.z, dl4.w)};
+        const float2 dup[2] = {make_float2(du4.x, du4.y), make_float2(du4.z, du4.w)};
+        const float2 dyp[2] = {make_float2(dy4.x, dy4.y), make_float2(dy4.z, dy4.w)};
+        float Bv[NPER], Cv[NPER];
+        lds_vec<NPER>(Bv, Bf + t * NPT);
+        lds_vec<NPER>(Cv, Cf + t * NPT);
+        float2 gs[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+        float2 S[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+        float2 bc[NPER];  // (dB, dC) partial of this thread's 4 channels, per state
+#pragma unroll
+        for (int j = 0; j < NPER; ++j) {
+          const float4 hc4 = hst[(t * NPER + j) * nscan_threads];
+          const float2 hc[2] = {make_float2(hc4.x, hc4.y), make_float2(hc4.z, hc4.w)};
+          const float2 Bb = make_float2(Bv[j], Bv[j]), Cb = make_float2(Cv[j], Cv[j]);
+          float2 db2 = make_float2(0.f, 0.f), dc2 = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const float2 ga = __fmul2_rn(dlp[q], A2[q][j]);
+            const float2 a = make_float2(ex2_approx(ga.x), ex2_approx(ga.y));
+            const float2 dh = __ffma2_rn(Cb, dyp[q], dhc[q][j]);
+            dc2 = __ffma2_rn(dyp[q], hc[q], dc2);
+            const float2 ndu = make_float2(-dup[q].x, -dup[q].y);
+            const float2 hm = __ffma2_rn(ndu, Bb, hc[q]);  // a_t * h_{t-1} = h_t - delta*u*B
+            const float2 g = __fmul2_rn(dh, hm);            // dL/d(delta*A) for these two (d, n)
+            gs[q] = __ffma2_rn(g, A2[q][j], gs[q]);
+            dAacc[q][j] = __ffma2_rn(g, dlp[q], dAacc[q][j]);
+            S[q] = __ffma2_rn(dh, Bb, S[q]);
+            db2 = __ffma2_rn(dh, dup[q], db2);
+            dhc[q][j] = __fmul2_rn(a, dh);
+          }
+          bc[j] = make_float2(db2.x + db2.y, dc2.x + dc2.y);
+        }
+        // sums over this warp's state-lanes (lane bits 3, 4), then one partial per warp
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          gs[q] = __fadd2_rn(gs[q], shfl_xor2(gs[q], 8));
+          S[q] = __fadd2_rn(S[q], shfl_xor2(S[q], 8));
+          gs[q] = __fadd2_rn(gs[q], shfl_xor2(gs[q], 16));
+          S[q] = __fadd2_rn(S[q], shfl_xor2(S[q], 16));
+        }
+        if (ln == 0) {
+          *reinterpret_cast<float4*>(pg + t * kBD) = make_float4(gs[0].x, gs[0].y, gs[1].x, gs[1].y);
+          *reinterpret_cast<float4*>(pS + t * kBD) = make_float4(S[0].x, S[0].y, S[1].x, S[1].y);
+        }
+        // sums over the warp's channel-lanes (lane bits 0..2)
+#pragma unroll
+        for (int j = 0; j < NPER; ++j) {
+          bc[j] = __fadd2_rn(bc[j], shfl_xor2(bc[j], 1));
+          bc[j] = __fadd2_rn(bc[j], shfl_xor2(bc[j], 2));
+          bc[j] = __fadd2_rn(bc[j], shfl_xor2(bc[j], 4));
+        }
+        if (ld == 0) {
+          float vb[NPER], vc[NPER];
+#pragma unroll
+          for (int j = 0; j < NPER; ++j) vb[j] = bc[j].x, vc[j] = bc[j].y;
+          sts_vec<NPER>(redB + t * NPT, vb);
+          sts_vec<NPER>(redC + t * NPT, vc);
+        }
+      }
+      bar_arrive(3 + ws, bar_count);  // chunk c swept
+      rslot = (rslot + 1 == kBRing) ? 0 : rslot + 1;
+    }
+    // ---- epilogue: dA partial of this batch element -----------------------------------------------------------
+#pragma unroll
+    for (int j = 0; j < NPER; ++j) {
+      const int n = nbase + j;
+      if (n < p.N) {
+        float* dst = p.ws_dA + ((int64_t)b * p.N + n) * p.D + d0 + dl0;
+        const float v[4] = {dAacc[0][j].x, dAacc[0][j].y, dAacc[1][j].x, dAacc[1][j].y};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (dl0 + i < dvalid) dst[i] = v[i];
+      }
+    }
+    return;
+  }
+
+  // =========================================== HELPER WARPS ===============================================
+  const int ht = tid - nscan_threads;  // 0..127
   const bool do_softplus = p.flags & MAMBA_FLAG_DELTA_SOFTPLUS;
-  const int nbase = (w * 4 + ln) * NPER;  // first state of this thread
-  const int dl0 = 4 * ld;                 // first (tile-local) channel of this thread
-
-  // ---- carve shared memory ---------------------------------------------------------------
-  const int raw_stage_elems = 4 * CK * kBD + 2 * CK * NPT;
-  T* raw = reinterpret_cast<T*>(smem_raw);
-  size_t off = (size_t)2 * raw_stage_elems * sizeof(T);
-  off = (off + 15) & ~(size_t)15;
-  float* wdl = reinterpret_cast<float*>(smem_raw + off);  // [CK][32] softplus(delta)
-  float* wdu = wdl + CK * kBD;                            // delta * u
-  float* wdy = wdu + CK * kBD;                            // dout * silu(z)
-  float* wB = wdy + CK * kBD;                             // [CK][NPT]
-  float* wC = wB + CK * NPT;
-  float* pg = wC + CK * NPT;         // [NW][CK][32]  sum_n g*A2   (d_delta through exp)
-  float* pS = pg + NW * CK * kBD;    // [NW][CK][32]  sum_n dh*B
-  float* py = pS + NW * CK * kBD;    // [NW][CK][32]  sum_n h*C    (only if has_z)
-  float* redB = py + NW * CK * kBD;  // [CK][NPT]     sum_d dh * delta*u over the CTA's channels
-  float* redC = redB + CK * NPT;     // [CK][NPT]     sum_d dy * h
-  float* fin = redC + CK * NPT;      // [2][nwarps][32] final dD / d_bias cross-warp reduction
-  float4* hs = reinterpret_cast<float4*>(fin + 2 * kBMaxWarps * 32);  // [CK][NPER][nthreads] float4 (4 channels)
-
-  struct Stage {
-    T *u, *dl, *z, *dout, *Bm, *Cm;
-  };
-  auto stage = [&](int st) {
-    Stage r;
-    T* base = raw + (size_t)st * raw_stage_elems;
-    r.u = base;
-    r.dl = r.u + CK * kBD;
-    r.z = r.dl + CK * kBD;
-    r.dout = r.z + CK * kBD;
-    r.Bm = r.dout + CK * kBD;
-    r.Cm = r.Bm + CK * NPT;
-    return r;
-  };
-
+  const int my_t = ht >> 3, my_c = 4 * (ht & 7);  // this thread's (timestep, 4 channels) of every chunk
+  float bias4[4], D4[4], dD_acc[4], db_acc[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int d = d0 + my_c + e;
+    bias4[e] = ((p.flags & MAMBA_FLAG_HAS_DELTA_BIAS) && d < p.D) ? p.dbias[d] : 0.f;
+    D4[e] = ((p.flags & MAMBA_FLAG_HAS_D) && d < p.D) ? p.Dv[d] : 0.f;
+    dD_acc[e] = 0.f, db_acc[e] = 0.f;
+  }
   const T* gu = static_cast<const T*>(p.u) + (int64_t)b * p.u_bs + d0;
   const T* gdl = static_cast<const T*>(p.delta) + (int64_t)b * p.delta_bs + d0;
   const T* gz = has_z ? static_cast<const T*>(p.z) + (int64_t)b * p.z_bs + d0 : nullptr;
+  const T* gyp = has_z ? static_cast<const T*>(p.ypre) + (int64_t)b * p.ypre_bs + d0 : nullptr;
   const T* gdo = static_cast<const T*>(p.dout) + (int64_t)b * p.dout_bs + d0;
   const T* gB = static_cast<const T*>(p.Bm) + (int64_t)b * p.B_bs;
   const T* gC = static_cast<const T*>(p.Cm) + (int64_t)b * p.C_bs;
 
-  auto issue_loads = [&](int st, int c) {
-    Stage r = stage(st);
-    const int t0 = c * CK;
-    const int rv = min(CK, p.L - t0);
-    load_tile_async<T>(r.u, kBD, gu + (int64_t)t0 * p.u_ls, p.u_ls, CK, rv, dvalid, p.vec_u, tid, nthreads);
-    load_tile_async<T>(r.dl, kBD, gdl + (int64_t)t0 * p.delta_ls, p.delta_ls, CK, rv, dvalid, p.vec_delta, tid,
-                       nthreads);
-    if (has_z) load_tile_async<T>(r.z, kBD, gz + (int64_t)t0 * p.z_ls, p.z_ls, CK, rv, dvalid, p.vec_z, tid, nthreads);
-    load_tile_async<T>(r.dout, kBD, gdo + (int64_t)t0 * p.dout_ls, p.dout_ls, CK, rv, dvalid, p.vec_dout, tid,
-                       nthreads);
-    load_tile_async<T>(r.Bm, NPT, gB + (int64_t)t0 * p.B_ls, p.B_ls, CK, rv, p.N, p.vec_B, tid, nthreads);
-    load_tile_async<T>(r.Cm, NPT, gC + (int64_t)t0 * p.C_ls, p.C_ls, CK, rv, p.N, p.vec_C, tid, nthreads);
+  auto issue_loads = [&](int it, int rslot) {
+    if (it < nck) {
+      const int c = nck - 1 - it;
+      unsigned char* base = raw_base + (size_t)rslot * lay.raw_bytes;
+      const int t0 = c * kCK;
+      const int rv = min(kCK, p.L - t0);
+      load_tile_async<T>(reinterpret_cast<T*>(base + lay.raw_u), kBD, gu + (int64_t)t0 * p.u_ls, p.u_ls, kCK, rv, dvalid,
+                         p.vec_u, ht, kBHelperThreads);
+      load_tile_async<T>(reinterpret_cast<T*>(base + lay.raw_dl), kBD, gdl + (int64_t)t0 * p.delta_ls, p.delta_ls, kCK, rv,
+                         dvalid, p.vec_delta, ht, kBHelperThreads);
+      load_tile_async<T>(reinterpret_cast<T*>(base + lay.raw_do), kBD, gdo + (int64_t)t0 * p.dout_ls, p.dout_ls, kCK, rv,
+                         dvalid, p.vec_dout, ht, kBHelperThreads);
+      if (has_z) {
+        load_tile_async<T>(reinterpret_cast<T*>(base + lay.raw_z), kBD, gz + (int64_t)t0 * p.z_ls, p.z_ls, kCK, rv, dvalid,
+                           p.vec_z, ht, kBHelperThreads);
+        load_tile_async<T>(reinterpret_cast<T*>(base + lay.raw_yp), kBD, gyp + (int64_t)t0 * p.ypre_ls, p.ypre_ls, kCK, rv,
+                           dvalid, p.vec_ypre, ht, kBHelperThreads);
+      }
+      load_tile_async<T>(reinterpret_cast<T*>(base + lay.raw_B), NPT, gB + (int64_t)t0 * p.B_ls, p.B_ls, kCK, rv, p.N,
+                         p.vec_B, ht, kBHelperThreads);
+      load_tile_async<T>(reinterpret_cast<T*>(base + lay.raw_C), NPT, gC + (int64_t)t0 * p.C_ls, p.C_ls, kCK, rv, p.N,
+                         p.vec_C, ht, kBHelperThreads);
+    }
+    cp_async_commit();
   };
 
-  // ---- per-thread constants, accumulators and carried adjoint state ----------------------
-  float A2[4][NPER], dAacc[4][NPER], dhc[4][NPER];
+  auto pre_pass = [&](int it, int rslot) {
+    const int c = nck - 1 - it;
+    unsigned char* rbase = raw_base + (size_t)rslot * lay.raw_bytes;
+    unsigned char* wbase = work_base + (size_t)(it & 1) * lay.work_bytes;
+    const int rv = min(kCK, p.L - c * kCK);
+    const int o = my_t * kBD + my_c;
+    float dl[4], uu[4], dy[4], du[4];
+    V4<T>::ld(reinterpret_cast<const T*>(rbase + lay.raw_dl) + o, dl);
+    V4<T>::ld(reinterpret_cast<const T*>(rbase + lay.raw_u) + o, uu);
+    V4<T>::ld(reinterpret_cast<const T*>(rbase + lay.raw_do) + o, dy);
+    if (has_z) {
+      float zz[4];
+      V4<T>::ld(reinterpret_cast<const T*>(rbase + lay.raw_z) + o, zz);
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < NPER; ++j) {
-      const int d = d0 + dl0 + i, n = nbase + j;
-      A2[i][j] = (d < p.D && n < p.N) ? p.A[(int64_t)d * p.N + n] * kLog2e : 0.f;
-      dAacc[i][j] = 0.f;
-      dhc[i][j] = 0.f;
+      for (int e = 0; e < 4; ++e) dy[e] *= silu_fast(zz[e]);
     }
-  // post-pass accumulators: this thread always handles tile-local channel `lane` there
-  const int dpp = d0 + lane;
-  const float bias_d = ((p.flags & MAMBA_FLAG_HAS_DELTA_BIAS) && dpp < p.D) ? p.dbias[dpp] : 0.f;
-  const float D_d = ((p.flags & MAMBA_FLAG_HAS_D) && dpp < p.D) ? p.Dv[dpp] : 0.f;
-  float dD_acc = 0.f, db_acc = 0.f;
-
-  const int nck = p.nck;
-  issue_loads((nck - 1) & 1, nck - 1);
-  cp_async_commit();
-
-  for (int c = nck - 1; c >= 0; --c) {
-    if (c > 0) issue_loads((c - 1) & 1, c - 1);
-    cp_async_commit();
-    cp_async_wait<1>();
-    __syncthreads();
-
-    Stage r = stage(c & 1);
-    const int t0 = c * CK;
-    const int rv = min(CK, p.L - t0);
-
-    // ---- pre-pass -------------------------------------------------------------------------
-    for (int i = tid; i < CK * kBD; i += nthreads) {  // i % 32 == lane
-      const int t = i >> 5;
-      float dl = 0.f, du = 0.f, dy = 0.f;
-      if (t < rv) {
-        dl = IO<T>::cvt(r.dl[i]) + bias_d;
-        if (do_softplus) dl = softplus_f(dl);
-        du = dl * IO<T>::cvt(r.u[i]);
-        dy = IO<T>::cvt(r.dout[i]);
-        if (has_z) dy *= silu_f(IO<T>::cvt(r.z[i]));
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float v = dl[e] + bias4[e];
+      if (do_softplus) v = softplus_fast(v);
+      if (my_t >= rv) v = 0.f, dy[e] = 0.f;  // padded timestep: contributes nothing
+      dl[e] = v, du[e] = v * uu[e];
+    }
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(wbase + lay.w_dl) + o) = make_float4(dl[0], dl[1], dl[2], dl[3]);
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(wbase + lay.w_du) + o) = make_float4(du[0], du[1], du[2], du[3]);
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(wbase + lay.w_dy) + o) = make_float4(dy[0], dy[1], dy[2], dy[3]);
+    if (sizeof(T) != 4) {
+      const T* sB = reinterpret_cast<const T*>(rbase + lay.raw_B);
+      const T* sC = reinterpret_cast<const T*>(rbase + lay.raw_C);
+      float* Bf = reinterpret_cast<float*>(wbase + lay.w_Bf);
+      float* Cf = reinterpret_cast<float*>(wbase + lay.w_Cf);
+      for (int i = ht; i < kCK * NPT; i += kBHelperThreads) {
+        Bf[i] = IO<T>::cvt(sB[i]);
+        Cf[i] = IO<T>::cvt(sC[i]);
       }
-      wdl[i] = dl, wdu[i] = du, wdy[i] = dy;
     }
-    for (int i = tid; i < CK * NPT; i += nthreads) {
-      wB[i] = IO<T>::cvt(r.Bm[i]);
-      wC[i] = IO<T>::cvt(r.Cm[i]);
-    }
-    __syncthreads();
+  };
 
-    // ---- chunk-start state from the checkpoint ---------------------------------------------
-    float h[4][NPER];
+  auto store4 = [&](void* base, int64_t bs, int64_t ls, int64_t tg, bool vec, const float (&v)[4]) {
+    T* o = static_cast<T*>(base) + (int64_t)b * bs + tg * ls + d0 + my_c;
+    if (vec && my_c + 4 <= dvalid) {
+      V4<T>::st_global(o, v);
+    } else {
 #pragma unroll
-    for (int j = 0; j < NPER; ++j) {
-      const int n = nbase + j;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (c > 0 && n < p.N) {
-        const float* ck = p.ckpt + (((int64_t)b * nck + c) * p.N + n) * p.D + d0 + dl0;
-        if (p.vec_ck && dl0 + 4 <= dvalid) {
-          v = *reinterpret_cast<const float4*>(ck);
-        } else {
-          if (dl0 + 0 < dvalid) v.x = ck[0];
-          if (dl0 + 1 < dvalid) v.y = ck[1];
-          if (dl0 + 2 < dvalid) v.z = ck[2];
-          if (dl0 + 3 < dvalid) v.w = ck[3];
+      for (int e = 0; e < 4; ++e)
+        if (my_c + e < dvalid) IO<T>::st(o + e, v[e]);
+    }
+  };
+
+  auto post_pass = [&](int it, int rslot) {
+    const int c = nck - 1 - it;
+    unsigned char* rbase = raw_base + (size_t)rslot * lay.raw_bytes;
+    unsigned char* wbase = work_base + (size_t)(it & 1) * lay.work_bytes;
+    const int t0 = c * kCK;
+    const int rv = min(kCK, p.L - t0);
+    if (my_t < rv) {
+      const int o = my_t * kBD + my_c;
+      const float* pg = reinterpret_cast<const float*>(wbase + lay.w_pg) + o;
+      const float* pS = reinterpret_cast<const float*>(wbase + lay.w_pS) + o;
+      float2 g01 = make_float2(0.f, 0.f), g23 = g01, S01 = g01, S23 = g01;
+      for (int w = 0; w < NW; ++w) {
+        const float4 a = *reinterpret_cast<const float4*>(pg + w * kCK * kBD);
+        const float4 s4 = *reinterpret_cast<const float4*>(pS + w * kCK * kBD);
+        g01 = __fadd2_rn(g01, make_float2(a.x, a.y)), g23 = __fadd2_rn(g23, make_float2(a.z, a.w));
+        S01 = __fadd2_rn(S01, make_float2(s4.x, s4.y)), S23 = __fadd2_rn(S23, make_float2(s4.z, s4.w));
+      }
+      const float g[4] = {g01.x, g01.y, g23.x, g23.y}, S[4] = {S01.x, S01.y, S23.x, S23.y};
+      float uu[4], raw[4], go[4];
+      V4<T>::ld(reinterpret_cast<const T*>(rbase + lay.raw_u) + o, uu);
+      V4<T>::ld(reinterpret_cast<const T*>(rbase + lay.raw_dl) + o, raw);
+      V4<T>::ld(reinterpret_cast<const T*>(rbase + lay.raw_do) + o, go);
+      const float4 dl4 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(wbase + lay.w_dl) + o);
+      const float4 dy4 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(wbase + lay.w_dy) + o);
+      const float dl[4] = {dl4.x, dl4.y, dl4.z, dl4.w}, dy[4] = {dy4.x, dy4.y, dy4.z, dy4.w};
+      float ddl[4], du[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float v = fmaf(uu[e], S[e], g[e] * kLn2);
+        if (do_softplus) {
+          const float x = raw[e] + bias4[e];
+          v *= x > 20.f ? 1.f : rcp_approx(1.f + ex2_approx(-x * kLog2e));  // softplus' = sigmoid
         }
+        ddl[e] = v;
+        du[e] = fmaf(dl[e], S[e], dy[e] * D4[e]);
+        dD_acc[e] = fmaf(dy[e], uu[e], dD_acc[e]);
+        db_acc[e] += v;
       }
-      h[0][j] = v.x, h[1][j] = v.y, h[2][j] = v.z, h[3][j] = v.w;
-    }
-    float h0[4][NPER];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < NPER; ++j) h0[i][j] = h[i][j];
-
-    // ---- forward recompute: h_t for every step of the chunk -> shared memory ------------------
-#pragma unroll 2
-    for (int t = 0; t < rv; ++t) {
-      const float4 dl4 = *reinterpret_cast<const float4*>(wdl + t * kBD + dl0);
-      const float4 du4 = *reinterpret_cast<const float4*>(wdu + t * kBD + dl0);
-      const float dl[4] = {dl4.x, dl4.y, dl4.z, dl4.w};
-      const float du[4] = {du4.x, du4.y, du4.z, du4.w};
-      float Bv[NPER], Cv[NPER];
-      lds_vec<NPER>(Bv, wB + t * NPT + nbase);
-      float yacc[4] = {0.f, 0.f, 0.f, 0.f};
-      if (has_z) lds_vec<NPER>(Cv, wC + t * NPT + nbase);
-#pragma unroll
-      for (int j = 0; j < NPER; ++j) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float a = ex2_approx(dl[i] * A2[i][j]);
-          h[i][j] = fmaf(a, h[i][j], du[i] * Bv[j]);
-          if (has_z) yacc[i] = fmaf(h[i][j], Cv[j], yacc[i]);
-        }
-        hs[(t * NPER + j) * nthreads + tid] = make_float4(h[0][j], h[1][j], h[2][j], h[3][j]);
-      }
+      store4(p.du, p.du_bs, p.du_ls, t0 + my_t, p.vec_du, du);
+      store4(p.ddelta, p.ddelta_bs, p.ddelta_ls, t0 + my_t, p.vec_ddelta, ddl);
       if (has_z) {
+        float zz[4], yp[4], dz[4];
+        V4<T>::ld(reinterpret_cast<const T*>(rbase + lay.raw_z) + o, zz);
+        V4<T>::ld(reinterpret_cast<const T*>(rbase + lay.raw_yp) + o, yp);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          yacc[i] += __shfl_xor_sync(0xffffffffu, yacc[i], 8);
-          yacc[i] += __shfl_xor_sync(0xffffffffu, yacc[i], 16);
+        for (int e = 0; e < 4; ++e) {
+          const float sg = rcp_approx(1.f + ex2_approx(-zz[e] * kLog2e));
+          dz[e] = go[e] * yp[e] * sg * fmaf(zz[e], 1.f - sg, 1.f);
         }
-        if (ln == 0)
-          *reinterpret_cast<float4*>(py + (w * CK + t) * kBD + dl0) = make_float4(yacc[0], yacc[1], yacc[2], yacc[3]);
-      }
-    }
-
-    // ---- reverse sweep: adjoint recurrence -----------------------------------------------------
-    // each thread re-reads only what it wrote to hs itself, so no barrier is needed in between.
-#pragma unroll 1
-    for (int t = rv - 1; t >= 0; --t) {
-      const float4 dl4 = *reinterpret_cast<const float4*>(wdl + t * kBD + dl0);
-      const float4 du4 = *reinterpret_cast<const float4*>(wdu + t * kBD + dl0);
-      const float4 dy4 = *reinterpret_cast<const float4*>(wdy + t * kBD + dl0);
-      const float dl[4] = {dl4.x, dl4.y, dl4.z, dl4.w};
-      const float du[4] = {du4.x, du4.y, du4.z, du4.w};
-      const float dy[4] = {dy4.x, dy4.y, dy4.z, dy4.w};
-      float Bv[NPER], Cv[NPER];
-      lds_vec<NPER>(Bv, wB + t * NPT + nbase);
-      lds_vec<NPER>(Cv, wC + t * NPT + nbase);
-      float gs[4] = {0.f, 0.f, 0.f, 0.f}, S[4] = {0.f, 0.f, 0.f, 0.f};
-      float dBp[NPER], dCp[NPER];
-#pragma unroll
-      for (int j = 0; j < NPER; ++j) {
-        const float4 hc4 = hs[(t * NPER + j) * nthreads + tid];
-        float4 hp4;
-        if (t > 0)
-          hp4 = hs[((t - 1) * NPER + j) * nthreads + tid];
-        else
-          hp4 = make_float4(h0[0][j], h0[1][j], h0[2][j], h0[3][j]);
-        const float hc[4] = {hc4.x, hc4.y, hc4.z, hc4.w};
-        const float hp[4] = {hp4.x, hp4.y, hp4.z, hp4.w};
-        float db = 0.f, dc = 0.f;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float a = ex2_approx(dl[i] * A2[i][j]);
-          const float dh = fmaf(Cv[j], dy[i], dhc[i][j]);
-          dc = fmaf(dy[i], hc[i], dc);
-          const float g = dh * hp[i] * a;  // dL/d(delta*A) for this (t, d, n)
-          gs[i] = fmaf(g, A2[i][j], gs[i]);
-          dAacc[i][j] = fmaf(g, dl[i], dAacc[i][j]);
-          S[i] = fmaf(dh, Bv[j], S[i]);
-          db = fmaf(dh, du[i], db);
-          dhc[i][j] = a * dh;
-        }
-        dBp[j] = db, dCp[j] = dc;
-      }
-      // sums over this warp's state-lanes (lane bits 3,4)
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        gs[i] += __shfl_xor_sync(0xffffffffu, gs[i], 8);
-        gs[i] += __shfl_xor_sync(0xffffffffu, gs[i], 16);
-        S[i] += __shfl_xor_sync(0xffffffffu, S[i], 8);
-        S[i] += __shfl_xor_sync(0xffffffffu, S[i], 16);
-      }
-      if (ln == 0) {
-        *reinterpret_cast<float4*>(pg + (w * CK + t) * kBD + dl0) = make_float4(gs[0], gs[1], gs[2], gs[3]);
-        *reinterpret_cast<float4*>(pS + (w * CK + t) * kBD + dl0) = make_float4(S[0], S[1], S[2], S[3]);
-      }
-      // sums over the warp's channel-lanes (lane bits 0..2)
-#pragma unroll
-      for (int j = 0; j < NPER; ++j) {
-#pragma unroll
-        for (int o = 1; o < 8; o <<= 1) {
-          dBp[j] += __shfl_xor_sync(0xffffffffu, dBp[j], o);
-          dCp[j] += __shfl_xor_sync(0xffffffffu, dCp[j], o);
-        }
-      }
-      if (ld == 0) {
-#pragma unroll
-        for (int j = 0; j < NPER; ++j) {
-          redB[t * NPT + nbase + j] = dBp[j];
-          redC[t * NPT + nbase + j] = dCp[j];
-        }
-      }
-    }
-    __syncthreads();
-
-    // ---- post-pass ------------------------------------------------------------------------------
-    for (int i = tid; i < CK * kBD; i += nthreads) {  // i % 32 == lane
-      const int t = i >> 5;
-      if (t < rv && dpp < p.D) {
-        float g = 0.f, S = 0.f;
-        for (int ww = 0; ww < NW; ++ww) {
-          g += pg[ww * CK * kBD + i];
-          S += pS[ww * CK * kBD + i];
-        }
-        const float uu = IO<T>::cvt(r.u[i]);
-        const float dy = wdy[i];
-        float ddl = fmaf(uu, S, g * kLn2);
-        if (do_softplus) ddl *= softplus_grad_f(IO<T>::cvt(r.dl[i]) + bias_d);
-        const float du = fmaf(wdl[i], S, dy * D_d);
-        dD_acc = fmaf(dy, uu, dD_acc);
-        db_acc += ddl;
-        const int64_t tg = t0 + t;
-        IO<T>::st(static_cast<T*>(p.du) + (int64_t)b * p.du_bs + tg * p.du_ls + dpp, du);
-        IO<T>::st(static_cast<T*>(p.ddelta) + (int64_t)b * p.ddelta_bs + tg * p.ddelta_ls + dpp, ddl);
-        if (has_z) {
-          float y = 0.f;
-          for (int ww = 0; ww < NW; ++ww) y += py[ww * CK * kBD + i];
-          y = fmaf(D_d, uu, y);
-          const float zz = IO<T>::cvt(r.z[i]);
-          const float sg = sigmoid_f(zz);
-          const float dz = IO<T>::cvt(r.dout[i]) * y * sg * fmaf(zz, 1.f - sg, 1.f);
-          IO<T>::st(static_cast<T*>(p.dz) + (int64_t)b * p.dz_bs + tg * p.dz_ls + dpp, dz);
-        }
+        store4(p.dz, p.dz_bs, p.dz_ls, t0 + my_t, p.vec_dz, dz);
       }
     }
     // per-CTA partial of dB / dC for this chunk -> workspace [B][ntiles][L][N]
     {
       float* wsB = p.ws_dB + (((int64_t)b * p.ntiles + tile) * p.L + t0) * p.N;
       float* wsC = p.ws_dC + (((int64_t)b * p.ntiles + tile) * p.L + t0) * p.N;
-      for (int i = tid; i < rv * p.N; i += nthreads) {
-        const int t = i / p.N, n = i - t * p.N;
-        wsB[i] = redB[t * NPT + n];
-        wsC[i] = redC[t * NPT + n];
+      const float* redB = reinterpret_cast<const float*>(wbase + lay.w_rB);
+      const float* redC = reinterpret_cast<const float*>(wbase + lay.w_rC);
+      if (NPT == p.N && (p.N & 3) == 0) {
+        const int nv = rv * p.N / 4;
+        for (int i = ht; i < nv; i += kBHelperThreads) {
+          reinterpret_cast<float4*>(wsB)[i] = reinterpret_cast<const float4*>(redB)[i];
+          reinterpret_cast<float4*>(wsC)[i] = reinterpret_cast<const float4*>(redC)[i];
+        }
+      } else {
+        for (int i = ht; i < rv * p.N; i += kBHelperThreads) {
+          const int t = i / p.N, n = i - t * p.N;
+          wsB[i] = redB[t * NPT + n];
+          wsC[i] = redC[t * NPT + n];
+        }
       }
     }
-    __syncthreads();
-  }
+  };
 
-  // ---- epilogue: dA partial, dD / d_bias partials ------------------------------------------------
-#pragma unroll
-  for (int j = 0; j < NPER; ++j) {
-    const int n = nbase + j;
-    if (n < p.N) {
-      float* dst = p.ws_dA + ((int64_t)b * p.N + n) * p.D + d0 + dl0;
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        if (dl0 + i < dvalid) dst[i] = dAacc[i][j];
+  // prologue
+  for (int it = 0; it < kBRing - 1; ++it) issue_loads(it, it);
+  int rslot = 0, pslot = kBRing - 1;
+  for (int it = 0; it < nck; ++it) {
+    cp_async_wait<kBRing - 2>();
+    bar_sync(5, kBHelperThreads);
+    pre_pass(it, rslot);
+    bar_arrive(1 + (it & 1), bar_count);  // READY
+    if (it >= 1) {
+      bar_sync(3 + ((it - 1) & 1), bar_count);  // DONE of the previous chunk
+      post_pass(it - 1, pslot);
     }
+    bar_sync(5, kBHelperThreads);
+    issue_loads(it + kBRing - 1, pslot);
+    pslot = rslot;
+    rslot = (rslot + 1 == kBRing) ? 0 : rslot + 1;
   }
-  fin[w * 32 + lane] = dD_acc;
-  fin[(kBMaxWarps + w) * 32 + lane] = db_acc;
-  __syncthreads();
-  if (w == 0 && dpp < p.D) {
+  bar_sync(3 + ((nck - 1) & 1), bar_count);
+  post_pass(nck - 1, pslot);
+
+  // ---- dD / d_bias: sum this CTA's 16 timestep-rows in shared memory, one partial per (b, d) ------------------
+  bar_sync(5, kBHelperThreads);
+  float* fin = reinterpret_cast<float*>(work_base);  // [2][16][32], the work slots are free now
+  *reinterpret_cast<float4*>(fin + my_t * kBD + my_c) = make_float4(dD_acc[0], dD_acc[1], dD_acc[2], dD_acc[3]);
+  *reinterpret_cast<float4*>(fin + (kCK + my_t) * kBD + my_c) = make_float4(db_acc[0], db_acc[1], db_acc[2], db_acc[3]);
+  bar_sync(5, kBHelperThreads);
+  if (ht < kBD && d0 + ht < p.D) {
     float sD = 0.f, sb = 0.f;
-    for (int ww = 0; ww < NW; ++ww) {
-      sD += fin[ww * 32 + lane];
-      sb += fin[(kBMaxWarps + ww) * 32 + lane];
+    for (int r = 0; r < kCK; ++r) {
+      sD += fin[r * kBD + ht];
+      sb += fin[(kCK + r) * kBD + ht];
     }
-    p.ws_dD[(int64_t)b * p.D + dpp] = sD;
-    p.ws_db[(int64_t)b * p.D + dpp] = sb;
+    p.ws_dD[(int64_t)b * p.D + d0 + ht] = sD;
+    p.ws_db[(int64_t)b * p.D + d0 + ht] = sb;
   }
 }
 
@@ -417,12 +555,10 @@ __global__ void scan_bwd_finalize_kernel(const ScanBwdParams p, int rows_per_blo
   }
 }
 
-static size_t bwd_smem_bytes(size_t elt, int CK, int NPER, int NW, int NPT) {
-  size_t raw = (size_t)2 * (4 * CK * kBD + 2 * CK * NPT) * elt;
-  raw = (raw + 15) & ~(size_t)15;
-  size_t work = (size_t)4 * (3 * CK * kBD + 2 * CK * NPT + 3 * (size_t)NW * CK * kBD + 2 * CK * NPT + 2 * kBMaxWarps * 32);
-  size_t hs = (size_t)16 * CK * NPER * NW * 32;
-  return raw + work + hs;
+template <typename T>
+static size_t bwd_smem_bytes(int NW, int NPT, int NPER) {
+  const BwdLayout<T> lay(NW, NPT, NPER);
+  return (size_t)kBRing * lay.raw_bytes + (size_t)2 * lay.work_bytes + lay.hs_bytes;
 }
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -439,16 +575,20 @@ static size_t bwd_workspace_layout(int B, int L, int D, int N, size_t* o_dB, siz
   return off;
 }
 
-template <typename T, int NPER, int CK>
+template <typename T, int NPER, int NW>
 static int launch_bwd(const ScanBwdParams& p, cudaStream_t stream) {
-  const size_t smem = bwd_smem_bytes(sizeof(T), CK, NPER, p.NW, p.NPT);
+  const size_t smem = bwd_smem_bytes<T>(NW, p.NPT, NPER);
   if (smem > 227 * 1024)
-    return set_error(MAMBA_ESIZE, "scan_bwd: d_state %d needs %zu B of shared memory (chunk %d)", p.N, smem, CK);
-  auto kern = scan_bwd_kernel<T, NPER, CK>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return set_error(MAMBA_ELAUNCH, "scan_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    return set_error(MAMBA_ESIZE, "scan_bwd: d_state %d needs %zu B of shared memory", p.N, smem);
+  auto kern = scan_bwd_kernel<T, NPER, NW>;
+  static thread_local size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_error(MAMBA_ELAUNCH, "scan_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    configured = smem;
+  }
   dim3 grid(p.ntiles, p.B);
-  kern<<<grid, p.NW * 32, smem, stream>>>(p);
+  kern<<<grid, (NW + kBHelperWarps) * 32, smem, stream>>>(p);
   count_launch();
   int rc = check_launch("scan_bwd");
   if (rc) return rc;
@@ -461,24 +601,26 @@ static int launch_bwd(const ScanBwdParams& p, cudaStream_t stream) {
 }
 
 template <typename T, int NPER>
-static int bwd_dispatch_ck(const ScanBwdParams& p, int chunk, cudaStream_t stream) {
-  switch (chunk) {
-    case 8: return launch_bwd<T, NPER, 8>(p, stream);
-    case 16: return launch_bwd<T, NPER, 16>(p, stream);
+static int bwd_dispatch_nw(const ScanBwdParams& p, cudaStream_t stream) {
+  switch (p.NW) {
+    case 1: return launch_bwd<T, NPER, 1>(p, stream);
+    case 2: return launch_bwd<T, NPER, 2>(p, stream);
+    case 3: case 4: return launch_bwd<T, NPER, 4>(p, stream);
+    case 5: case 6: case 7: case 8: return launch_bwd<T, NPER, 8>(p, stream);
   }
-  return set_error(MAMBA_EINVAL, "scan_bwd: chunk must be 8 or 16 (got %d)", chunk);
+  return set_error(MAMBA_ESIZE, "scan_bwd: d_state %d too large (max %d)", p.N, kBMaxWarps * 16);
 }
 
 template <typename T>
-static int bwd_dispatch(ScanBwdParams& p, int nper, int chunk, cudaStream_t stream) {
+static int bwd_dispatch(ScanBwdParams& p, int nper, cudaStream_t stream) {
   p.NW = ceil_div(p.N, 4 * nper);
-  const int np = p.NW * 4 * nper;
-  p.NPT = (np + 7) & ~7;
   if (p.NW > kBMaxWarps) return set_error(MAMBA_ESIZE, "scan_bwd: d_state %d too large (max %d)", p.N, kBMaxWarps * 16);
+  p.NW = p.NW <= 2 ? p.NW : (p.NW <= 4 ? 4 : 8);  // instantiated warp counts
+  p.NPT = (p.NW * 4 * nper + 7) & ~7;
   switch (nper) {
-    case 1: return bwd_dispatch_ck<T, 1>(p, chunk, stream);
-    case 2: return bwd_dispatch_ck<T, 2>(p, chunk, stream);
-    case 4: return bwd_dispatch_ck<T, 4>(p, chunk, stream);
+    case 1: return bwd_dispatch_nw<T, 1>(p, stream);
+    case 2: return bwd_dispatch_nw<T, 2>(p, stream);
+    case 4: return bwd_dispatch_nw<T, 4>(p, stream);
   }
   return set_error(MAMBA_EINVAL, "scan_bwd: variant must be 0, 1, 2 or 4 (got %d)", nper);
 }
@@ -505,8 +647,10 @@ extern "C" int mamba_scan_bwd(const MambaScanBwdArgs* a, void* stream) {
   if (a->batch > 65535) return set_error(MAMBA_ESIZE, "scan_bwd: batch %d above 65535", a->batch);
   if (!a->u || !a->delta || !a->A || !a->B || !a->C || !a->dout || !a->du || !a->ddelta || !a->dB || !a->dC || !a->dA)
     return set_error(MAMBA_EINVAL, "scan_bwd: null input or output pointer");
+  if (a->chunk != kCK) return set_error(MAMBA_EINVAL, "scan_bwd: chunk must be %d (got %d)", kCK, a->chunk);
   if (a->seqlen > a->chunk && !a->ckpt) return set_error(MAMBA_EINVAL, "scan_bwd: ckpt == NULL");
-  if ((a->flags & MAMBA_FLAG_HAS_Z) && (!a->z || !a->dz)) return set_error(MAMBA_EINVAL, "scan_bwd: HAS_Z but z/dz NULL");
+  if ((a->flags & MAMBA_FLAG_HAS_Z) && (!a->z || !a->dz || !a->y_pre))
+    return set_error(MAMBA_EINVAL, "scan_bwd: HAS_Z but z/dz/y_pre NULL");
   if ((a->flags & MAMBA_FLAG_HAS_D) && !a->D) return set_error(MAMBA_EINVAL, "scan_bwd: HAS_D but D == NULL");
   if ((a->flags & MAMBA_FLAG_HAS_DELTA_BIAS) && !a->delta_bias)
     return set_error(MAMBA_EINVAL, "scan_bwd: HAS_DELTA_BIAS but delta_bias == NULL");
@@ -514,12 +658,13 @@ extern "C" int mamba_scan_bwd(const MambaScanBwdArgs* a, void* stream) {
 
   ScanBwdParams p{};
   p.B = a->batch, p.L = a->seqlen, p.D = a->dim, p.N = a->dstate, p.flags = a->flags;
-  p.nck = ceil_div(p.L, a->chunk);
+  p.nck = ceil_div(p.L, kCK);
   p.ntiles = ceil_div(p.D, kBD);
-  p.u = a->u, p.delta = a->delta, p.Bm = a->B, p.Cm = a->C, p.z = a->z, p.dout = a->dout;
+  p.u = a->u, p.delta = a->delta, p.Bm = a->B, p.Cm = a->C, p.z = a->z, p.dout = a->dout, p.ypre = a->y_pre;
   p.u_bs = a->u_bs, p.u_ls = a->u_ls, p.delta_bs = a->delta_bs, p.delta_ls = a->delta_ls;
   p.B_bs = a->B_bs, p.B_ls = a->B_ls, p.C_bs = a->C_bs, p.C_ls = a->C_ls;
   p.z_bs = a->z_bs, p.z_ls = a->z_ls, p.dout_bs = a->dout_bs, p.dout_ls = a->dout_ls;
+  p.ypre_bs = a->y_pre_bs, p.ypre_ls = a->y_pre_ls;
   p.du = a->du, p.ddelta = a->ddelta, p.dz = a->dz, p.dB = a->dB, p.dC = a->dC;
   p.du_bs = a->du_bs, p.du_ls = a->du_ls, p.ddelta_bs = a->ddelta_bs, p.ddelta_ls = a->ddelta_ls;
   p.dz_bs = a->dz_bs, p.dz_ls = a->dz_ls, p.dB_bs = a->dB_bs, p.dB_ls = a->dB_ls, p.dC_bs = a->dC_bs, p.dC_ls = a->dC_ls;
@@ -540,15 +685,18 @@ extern "C" int mamba_scan_bwd(const MambaScanBwdArgs* a, void* stream) {
   p.vec_u = bvec_ok(a->u, a->u_bs, a->u_ls, elt);
   p.vec_delta = bvec_ok(a->delta, a->delta_bs, a->delta_ls, elt);
   p.vec_z = a->z ? bvec_ok(a->z, a->z_bs, a->z_ls, elt) : 0;
+  p.vec_ypre = a->y_pre ? bvec_ok(a->y_pre, a->y_pre_bs, a->y_pre_ls, elt) : 0;
   p.vec_dout = bvec_ok(a->dout, a->dout_bs, a->dout_ls, elt);
   p.vec_B = bvec_ok(a->B, a->B_bs, a->B_ls, elt);
   p.vec_C = bvec_ok(a->C, a->C_bs, a->C_ls, elt);
+  p.vec_du = bvec_ok(a->du, a->du_bs, a->du_ls, elt);
+  p.vec_ddelta = bvec_ok(a->ddelta, a->ddelta_bs, a->ddelta_ls, elt);
+  p.vec_dz = a->dz ? bvec_ok(a->dz, a->dz_bs, a->dz_ls, elt) : 0;
   p.vec_ck = a->ckpt && aligned16(a->ckpt) && (p.D % 4 == 0);
 
   int nper = a->variant;
-  if (nper == 0) nper = p.N >= 64 ? 4 : (p.N >= 32 ? 2 : 1);
+  if (nper == 0) nper = p.N <= 16 ? 1 : (p.N <= 32 ? 2 : 4);  // at most 4 scan warps: keeps the per-warp partials small
   while (nper < 4 && ceil_div(p.N, 4 * nper) > kBMaxWarps) nper *= 2;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  return a->dtype == MAMBA_F32 ? bwd_dispatch<float>(p, nper, a->chunk, st)
-                               : bwd_dispatch<__nv_bfloat16>(p, nper, a->chunk, st);
+  return a->dtype == MAMBA_F32 ? bwd_dispatch<float>(p, nper, st) : bwd_dispatch<__nv_bfloat16>(p, nper, st);
 }

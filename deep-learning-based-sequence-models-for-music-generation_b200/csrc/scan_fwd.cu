@@ -38,65 +38,9 @@ struct ScanFwdParams {
   int64_t u_bs, u_ls, delta_bs, delta_ls, B_bs, B_ls, C_bs, C_ls, z_bs, z_ls, out_bs, out_ls;
   const float *A, *Dv, *dbias, *h_init;
   float *ckpt, *h_last;
-  int vec_u, vec_delta, vec_z, vec_B, vec_C, vec_out;
-};
-
-// ---- fast transcendental helpers (MUFU ex2 / lg2 / rcp; relative error ~1e-7, far inside rtol 1e-4) ----------
-__device__ __forceinline__ float lg2_approx(float x) {
-  float y;
-  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float rcp_approx(float x) {
-  float y;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-// softplus with torch's threshold (x > 20 -> x).  For x < -4 the series of log1p(e) avoids the cancellation
-// of forming 1 + e in fp32.
-__device__ __forceinline__ float softplus_fast(float x) {
-  const float e = ex2_approx(x * kLog2e);
-  const float series = e * fmaf(e, fmaf(e, fmaf(e, -0.25f, 0.33333334f), -0.5f), 1.f);
-  const float full = lg2_approx(1.f + e) * kLn2;
-  const float r = x < -4.f ? series : full;
-  return x > 20.f ? x : r;
-}
-__device__ __forceinline__ float silu_fast(float x) { return x * rcp_approx(1.f + ex2_approx(-x * kLog2e)); }
-
-// Shared-memory store issued through asm so that nvvm does not order later shared loads behind it.
-__device__ __forceinline__ void sts_f32(float* p, float v) {
-  asm volatile("st.shared.f32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "f"(v));
-}
-__device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
-__device__ __forceinline__ void bar_arrive(int id, int count) {
-  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
-}
-
-// 4 consecutive elements of T <-> 4 floats
-template <typename T>
-struct V4;
-template <>
-struct V4<float> {
-  static __device__ __forceinline__ void ld(const float* p, float (&v)[4]) {
-    const float4 t = *reinterpret_cast<const float4*>(p);
-    v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w;
-  }
-  static __device__ __forceinline__ void st_global(float* p, const float (&v)[4]) { st_cs_f4(p, make_float4(v[0], v[1], v[2], v[3])); }
-};
-template <>
-struct V4<__nv_bfloat16> {
-  static __device__ __forceinline__ void ld(const __nv_bfloat16* p, float (&v)[4]) {
-    const uint2 t = *reinterpret_cast<const uint2*>(p);
-    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&t.x);
-    const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&t.y);
-    v[0] = __low2float(a), v[1] = __high2float(a), v[2] = __low2float(b), v[3] = __high2float(b);
-  }
-  static __device__ __forceinline__ void st_global(__nv_bfloat16* p, const float (&v)[4]) {
-    const __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
-    uint2 t;
-    t.x = *reinterpret_cast<const uint32_t*>(&a), t.y = *reinterpret_cast<const uint32_t*>(&b);
-    *reinterpret_cast<uint2*>(p) = t;
-  }
+  void* ypre;
+  int64_t ypre_bs, ypre_ls;
+  int vec_u, vec_delta, vec_z, vec_B, vec_C, vec_out, vec_ypre;
 };
 
 // Shared-memory layout.  RAW ring slot (cp.async targets, element type T):
@@ -366,6 +310,16 @@ __global__ void __launch_bounds__((kMaxScanWarps + kHelperWarps) * 32) scan_fwd_
     V4<T>::ld(reinterpret_cast<const T*>(rbase + lay.raw_u) + my_t * kDT + my_c, uu);
 #pragma unroll
     for (int e = 0; e < 4; ++e) y[e] = fmaf(D4[e], uu[e], y[e]);
+    if (p.ypre != nullptr) {  // pre-gate output, kept for the backward's dz
+      T* yo = static_cast<T*>(p.ypre) + (int64_t)b * p.ypre_bs + (int64_t)(t0 + my_t) * p.ypre_ls + d0 + my_c;
+      if (p.vec_ypre && my_c + 4 <= dvalid) {
+        V4<T>::st_global(yo, y);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (my_c + e < dvalid) IO<T>::st(yo + e, y[e]);
+      }
+    }
     if (has_z) {
       float zz[4];
       V4<T>::ld(reinterpret_cast<const T*>(rbase + lay.raw_z) + my_t * kDT + my_c, zz);
@@ -494,6 +448,8 @@ extern "C" int mamba_scan_fwd(const MambaScanFwdArgs* a, void* stream) {
   p.vec_B = vec_ok(a->B, a->B_bs, a->B_ls, elt);
   p.vec_C = vec_ok(a->C, a->C_bs, a->C_ls, elt);
   p.vec_out = vec_ok(a->out, a->out_bs, a->out_ls, elt);
+  p.ypre = a->y_pre, p.ypre_bs = a->y_pre_bs, p.ypre_ls = a->y_pre_ls;
+  p.vec_ypre = a->y_pre ? vec_ok(a->y_pre, a->y_pre_bs, a->y_pre_ls, elt) : 0;
 
   int nper = a->variant;
   if (nper == 0) nper = p.N >= 64 ? 8 : 4;

@@ -84,7 +84,7 @@ def _call(name, a, dev):
 # selective scan
 # ------------------------------------------------------------------------------------------------
 def _scan_fwd_raw(u, delta, A, B, C, D, z, delta_bias, delta_softplus, ckpt, chunk, h_init=None, h_last=None,
-                  variant=0):
+                  variant=0, y_pre=None):
     Bsz, L, Dm = u.shape
     N = A.shape[1]
     out = torch.empty((Bsz, L, Dm), dtype=u.dtype, device=u.device)
@@ -109,6 +109,8 @@ def _scan_fwd_raw(u, delta, A, B, C, D, z, delta_bias, delta_softplus, ckpt, chu
     a.ckpt = _p(ckpt)
     a.h_last = _p(h_last)
     a.h_init = _p(h_init)
+    if y_pre is not None:
+        a.y_pre, a.y_pre_bs, a.y_pre_ls = _p(y_pre), y_pre.stride(0), y_pre.stride(1)
     _call("mamba_scan_fwd", a, u.device)
     return out
 
@@ -129,12 +131,15 @@ class SelectiveScanFn(torch.autograd.Function):
         z = None if z is None else _rows(z.to(dt))
         A32, D32, b32 = _f32(A), _f32(D), _f32(delta_bias)
         need_grad = any(ctx.needs_input_grad[:8])
-        ckpt = None
+        ckpt = y_pre = None
         if need_grad and u.shape[1] > chunk:
             n = lib().mamba_scan_ckpt_elems(u.shape[0], u.shape[1], u.shape[2], A.shape[1], chunk)
             ckpt = torch.empty(n, dtype=torch.float32, device=u.device)
-        out = _scan_fwd_raw(u, delta, A32, B, C, D32, z, b32, delta_softplus, ckpt, chunk, variant=SCAN_FWD_VARIANT)
-        ctx.save_for_backward(u, delta, A32, B, C, D32, z, b32, ckpt)
+        if need_grad and z is not None:
+            y_pre = torch.empty(u.shape, dtype=u.dtype, device=u.device)  # pre-gate output, for dz
+        out = _scan_fwd_raw(u, delta, A32, B, C, D32, z, b32, delta_softplus, ckpt, chunk, variant=SCAN_FWD_VARIANT,
+                            y_pre=y_pre)
+        ctx.save_for_backward(u, delta, A32, B, C, D32, z, b32, ckpt, y_pre)
         ctx.delta_softplus = delta_softplus
         ctx.chunk = chunk
         ctx.in_dtypes = (A.dtype, None if D is None else D.dtype, None if delta_bias is None else delta_bias.dtype)
@@ -142,7 +147,7 @@ class SelectiveScanFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout):
-        u, delta, A, B, C, D, z, dbias, ckpt = ctx.saved_tensors
+        u, delta, A, B, C, D, z, dbias, ckpt, y_pre = ctx.saved_tensors
         Bsz, L, Dm = u.shape
         N = A.shape[1]
         dout = _rows(dout.to(u.dtype))
@@ -174,6 +179,7 @@ class SelectiveScanFn(torch.autograd.Function):
         if z is not None:
             a.z, a.z_bs, a.z_ls = _p(z), z.stride(0), z.stride(1)
             a.dz, a.dz_bs, a.dz_ls = _p(dz), dz.stride(0), dz.stride(1)
+            a.y_pre, a.y_pre_bs, a.y_pre_ls = _p(y_pre), y_pre.stride(0), y_pre.stride(1)
         a.delta_bias = _p(dbias)
         a.dout, a.dout_bs, a.dout_ls = _p(dout), dout.stride(0), dout.stride(1)
         a.ckpt = _p(ckpt)

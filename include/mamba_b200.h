@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define MAMBA_ABI_VERSION 1
+#define MAMBA_ABI_VERSION 2
 
 enum { MAMBA_F32 = 0, MAMBA_BF16 = 1 };
 
@@ -62,7 +62,7 @@ enum {
  * The [B, L, D, N] tensors deltaA / deltaB_u of the reference are never materialised.
  * When `ckpt` is non-null the state at the start of every `chunk`-timestep block is written to
  * it (fp32, layout [batch, nchunks, dstate, dim], nchunks = ceil(seqlen/chunk); slot 0 is not
- * written) for use by mamba_scan_bwd.  When `h_last` is non-null the final state h_{L-1} is
+ * written) for use by mamba_scan_bwd; with a z gate the backward also needs `y_pre`.  When `h_last` is non-null the final state h_{L-1} is
  * written to it ([batch, dim, dstate] fp32 — the decode step's `ssm_state` layout).
  * ------------------------------------------------------------------------------------------ */
 typedef struct MambaScanFwdArgs {
@@ -85,6 +85,8 @@ typedef struct MambaScanFwdArgs {
   float* ckpt;                                   /* see above, or NULL        */
   float* h_last;                                 /* [B, D, N] or NULL         */
   const float* h_init;                           /* [B, D, N] or NULL (zeros) */
+  void* y_pre;       int64_t y_pre_bs, y_pre_ls; /* [B, L, D] or NULL: the output BEFORE the z gate
+                                                    (scan + D*u), saved for mamba_scan_bwd's dz */
 } MambaScanFwdArgs;
 
 int mamba_scan_fwd(const MambaScanFwdArgs* args, void* stream);
@@ -128,6 +130,7 @@ typedef struct MambaScanBwdArgs {
   float* ddelta_bias; /* NULL iff !HAS_DELTA_BIAS */
   void* workspace;
   size_t workspace_bytes;
+  const void* y_pre; int64_t y_pre_bs, y_pre_ls; /* required iff HAS_Z: y_pre written by mamba_scan_fwd */
 } MambaScanBwdArgs;
 
 int mamba_scan_bwd(const MambaScanBwdArgs* args, void* stream);

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol(lib):
     for name in _declared_functions():
         assert hasattr(lib, name), f"libmamba_b200.so does not export {name}"
     assert set(_lib.EXPORTS) == set(_declared_functions())
-    assert lib.mamba_abi_version() == 1
+    assert lib.mamba_abi_version() == 2
 
 
 def test_ctypes_struct_layout_matches_c(tmp_path):

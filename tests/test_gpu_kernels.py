@@ -118,7 +118,10 @@ def test_scan_backward_fp32(shape, chunk):
     out.backward(dout.cuda())
     assert_close(out, ref, RTOL32, what=f"scan fwd (grad run) {shape}")
     for k in c:
-        assert_close(g[k].grad, c[k].grad, RTOL32, what=f"scan bwd d{k} {shape} chunk {chunk}")
+        # dA's reference is exactly 0 at L = 1 (h_{-1} = 0); the kernel forms a_t*h_{t-1} as h_t - delta*u*B, which
+        # leaves one rounding of that product behind: an absolute floor of 1e-6 (inputs are O(1)) covers it
+        assert_close(g[k].grad, c[k].grad, RTOL32, what=f"scan bwd d{k} {shape} chunk {chunk}",
+                     atol_abs=1e-6 if k == "A" else 0.0)
 
 
 def test_scan_backward_without_optional_inputs():

@@ -56,7 +56,10 @@ def test_mamba_block_forward_backward_fp32(cfg, L):
     assert_close(xg.grad, xc.grad, RTOL32, what="block dx")
     gp = dict(blk.named_parameters())
     for name, p in ref.named_parameters():
-        assert_close(gp[name].grad, p.grad, RTOL32, 2e-5, what=f"block d{name}")
+        # at L = 1 dA_log is exactly 0 in the reference; the kernel leaves one product rounding behind (see
+        # test_scan_backward_fp32), hence the absolute floor on that one gradient
+        assert_close(gp[name].grad, p.grad, RTOL32, 2e-5, what=f"block d{name}",
+                     atol_abs=1e-6 if name == "A_log" else 0.0)
 
 
 @pytest.mark.parametrize("layout", ["P", "S"])

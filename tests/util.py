@@ -2,13 +2,13 @@
 import torch
 
 
-def assert_close(got, ref, rtol, atol_frac=1e-5, what=""):
+def assert_close(got, ref, rtol, atol_frac=1e-5, what="", atol_abs=0.0):
     """|got - ref| <= atol + rtol*|ref| with atol = atol_frac * max|ref| (magnitude-aware floor)."""
     got = got.detach().float().cpu()
     ref = ref.detach().float().cpu()
     assert got.shape == ref.shape, f"{what}: shape {tuple(got.shape)} != {tuple(ref.shape)}"
     assert torch.isfinite(got).all(), f"{what}: non-finite values"
-    atol = atol_frac * float(ref.abs().max()) + 1e-30
+    atol = atol_frac * float(ref.abs().max()) + atol_abs + 1e-30
     err = (got - ref).abs()
     bound = atol + rtol * ref.abs()
     bad = err > bound
