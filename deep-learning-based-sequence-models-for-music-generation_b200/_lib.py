@@ -16,6 +16,7 @@ EXPORTS = [
     "mamba_conv1d_silu_fwd", "mamba_conv1d_silu_bwd", "mamba_conv1d_bwd_workspace_bytes",
     "mamba_conv_step", "mamba_ssm_step",
     "mamba_rmsnorm_fwd", "mamba_rmsnorm_bwd", "mamba_rmsnorm_bwd_workspace_bytes",
+    "mamba_filtered_ce_fwd", "mamba_filtered_ce_bwd", "mamba_filtered_ce_workspace_bytes",
 ]
 
 i32, i64, vp, fp, sz = C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_size_t
@@ -66,6 +67,14 @@ class NormArgs(C.Structure):
                 ("workspace_bytes", sz)]
 
 
+class LossArgs(C.Structure):
+    _fields_ = [("struct_size", i32), ("dtype", i32), ("batch", i32), ("seqlen", i32), ("vocab", i32),
+                ("boundaries", i32 * 4), ("reserved", i32),
+                ("logits", vp), ("logits_bs", i64), ("logits_ts", i64), ("src", vp), ("trg", vp), ("table", fp),
+                ("col_lse", fp), ("row_lse", fp), ("loss", fp), ("grad_out", fp),
+                ("dlogits", vp), ("dlogits_bs", i64), ("dlogits_ts", i64), ("workspace", vp), ("workspace_bytes", sz)]
+
+
 class MambaLibError(RuntimeError):
     pass
 
@@ -89,7 +98,8 @@ def lib() -> C.CDLL:
     for name, argt in (("mamba_scan_fwd", ScanFwdArgs), ("mamba_scan_bwd", ScanBwdArgs),
                        ("mamba_conv1d_silu_fwd", ConvArgs), ("mamba_conv1d_silu_bwd", ConvArgs),
                        ("mamba_conv_step", StepArgs), ("mamba_ssm_step", StepArgs),
-                       ("mamba_rmsnorm_fwd", NormArgs), ("mamba_rmsnorm_bwd", NormArgs)):
+                       ("mamba_rmsnorm_fwd", NormArgs), ("mamba_rmsnorm_bwd", NormArgs),
+                       ("mamba_filtered_ce_fwd", LossArgs), ("mamba_filtered_ce_bwd", LossArgs)):
         f = getattr(L, name)
         f.restype = C.c_int
         f.argtypes = [C.POINTER(argt), C.c_void_p]
@@ -99,6 +109,8 @@ def lib() -> C.CDLL:
     L.mamba_scan_bwd_workspace_bytes.argtypes = [C.c_int] * 4
     L.mamba_conv1d_bwd_workspace_bytes.restype = sz
     L.mamba_conv1d_bwd_workspace_bytes.argtypes = [C.c_int] * 4
+    L.mamba_filtered_ce_workspace_bytes.restype = sz
+    L.mamba_filtered_ce_workspace_bytes.argtypes = [C.c_int] * 3
     L.mamba_rmsnorm_bwd_workspace_bytes.restype = sz
     L.mamba_rmsnorm_bwd_workspace_bytes.argtypes = [C.c_int64, C.c_int]
     if L.mamba_abi_version() != 2:

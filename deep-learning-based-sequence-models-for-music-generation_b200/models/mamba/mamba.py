@@ -179,6 +179,40 @@ def _params_from_configs(d_model=None, n_layers=None, vocab_size=None, pad=False
                      metadata_vocab_size=cc.metadata_vocab_size)
 
 
+class _PaddedHeadFn(torch.autograd.Function):
+    """logits = x @ W^T computed as x @ pad8(W)^T (cuBLAS plumbing, no arithmetic of its own).  The gradient that
+    comes back from ops.filtered_ce_fn already lives in a zero-padded buffer of the same layout and is used in
+    place; any other gradient is padded first."""
+
+    @staticmethod
+    def forward(ctx, x, w, dt):
+        V, d = w.shape
+        Vp = V + (-V) % 8
+        wp = torch.zeros((Vp, d), dtype=dt, device=w.device)
+        wp[:V].copy_(w)
+        x2 = x.to(dt).reshape(-1, d)
+        out = torch.mm(x2, wp.t())                       # [rows, Vp]
+        ctx.save_for_backward(x2, wp)
+        ctx.meta = (x.shape, x.dtype, w.dtype, V, Vp)
+        return out.view(*x.shape[:-1], Vp)[..., :V]
+
+    @staticmethod
+    def backward(ctx, g):
+        x2, wp = ctx.saved_tensors
+        xshape, xdt, wdt, V, Vp = ctx.meta
+        rows = x2.shape[0]
+        g3 = g.reshape(-1, g.shape[-2], V) if g.dim() > 2 else g.reshape(1, -1, V)
+        if (g.dtype == wp.dtype and g3.stride(2) == 1 and g3.stride(1) == Vp and g3.stride(0) == g3.shape[1] * Vp
+                and g.storage_offset() == 0 and g.untyped_storage().nbytes() >= rows * Vp * g.element_size()):
+            gp = g.as_strided((rows, Vp), (Vp, 1))       # filtered_ce_fn's padded gradient, pad columns are zero
+        else:
+            gp = torch.zeros((rows, Vp), dtype=wp.dtype, device=g.device)
+            gp[:, :V].copy_(g.reshape(rows, V))
+        dx = torch.mm(gp, wp).view(xshape).to(xdt)
+        dw = torch.mm(gp.t(), x2)[:V].to(wdt)
+        return dx, dw, None
+
+
 class Mamba(nn.Module):
     """`Mamba(params)` -> Layout P (simple_mamba @L57-96);  `Mamba()` / `Mamba(d_model=1024, n_layers=10)` ->
     the shipped wrapper's layout (models/mamba/mamba.py:8-35)."""
@@ -230,7 +264,17 @@ class Mamba(nn.Module):
             normed, resid = layer.norm(hidden, resid)
             hidden = layer.mixer(normed)
         normed, _ = self.norm_f(hidden, resid)
-        return self.lm_head(normed[:, n_meta:])  # rows are independent: slicing before the GEMM == logits[:, 6:]
+        return self._head(normed[:, n_meta:])  # rows are independent: slicing before the GEMM == logits[:, 6:]
+
+    def _head(self, x):
+        """lm_head (layout P) with the vocabulary padded to a multiple of 8 INSIDE the GEMM: 17914 columns make
+        every row of the logits 4-byte aligned only, which pushes cuBLAS onto its slow align2 kernels.  The
+        returned tensor is the [.., :vocab] view of the padded product, so values and shape are unchanged."""
+        w = self.lm_head.weight
+        if w.shape[0] % 8 == 0 or not x.is_cuda:
+            return self.lm_head(x)
+        dt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else w.dtype
+        return _PaddedHeadFn.apply(x, w, dt)
 
     # ---- recurrent decode (no reference counterpart; SURVEY.md F3, §8 row A9) -------------------------
     def allocate_inference_cache(self, batch_size, max_seqlen=None, dtype=None):
@@ -252,7 +296,7 @@ class Mamba(nn.Module):
             normed, resid = layer.norm(hidden, resid)
             hidden = layer.mixer.prefill(normed, cs, hs)
         normed, _ = self.norm_f(hidden, resid)
-        return self.lm_head(normed[:, n_meta:])
+        return self._head(normed[:, n_meta:])
 
     @torch.no_grad()
     def step(self, token, cache):

@@ -19,7 +19,7 @@ import torch
 
 from . import _lib
 from ._lib import (FLAG_DELTA_SOFTPLUS, FLAG_HAS_D, FLAG_HAS_DELTA_BIAS, FLAG_HAS_Z, MAMBA_BF16, MAMBA_F32, ConvArgs,
-                   NormArgs, ScanBwdArgs, ScanFwdArgs, StepArgs, check, lib)
+                   LossArgs, NormArgs, ScanBwdArgs, ScanFwdArgs, StepArgs, check, lib)
 
 _DTYPES = {torch.float32: MAMBA_F32, torch.bfloat16: MAMBA_BF16}
 
@@ -379,6 +379,73 @@ def rmsnorm_fn(x, weight, residual=None, eps=1e-5, act_dtype=None):
     if stream is None:
         stream = residual if residual is not None else x
     return y, stream
+
+
+# ------------------------------------------------------------------------------------------------
+# grammar-masked loss (reference train.py:133-138 + :161-165)
+# ------------------------------------------------------------------------------------------------
+def _loss_args(logits, src, trg, table, boundaries, col_lse, row_lse, ws):
+    Bsz, T, V = logits.shape
+    a = LossArgs()
+    a.struct_size = ct.sizeof(LossArgs)
+    a.dtype = _dtype_code(logits)
+    a.batch, a.seqlen, a.vocab = Bsz, T, V
+    for i in range(4):
+        a.boundaries[i] = int(boundaries[i])
+    a.logits, a.logits_bs, a.logits_ts = _p(logits), logits.stride(0), logits.stride(1)
+    a.src, a.trg, a.table = _p(src), _p(trg), _p(table)
+    a.col_lse, a.row_lse = _p(col_lse), _p(row_lse)
+    a.workspace, a.workspace_bytes = _p(ws), ws.numel()
+    return a
+
+
+class FilteredCEFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, src, trg, table, boundaries):
+        _require_cuda(logits, src, trg, table)
+        if logits.dim() != 3 or logits.stride(2) != 1:
+            raise ValueError("filtered_ce: logits must be [B, T, V] with a contiguous vocab axis")
+        Bsz, T, V = logits.shape
+        if table.shape != (5, V) or table.dtype != torch.float32:
+            raise ValueError(f"filtered_ce: table must be fp32 [5, {V}]")
+        src = src.reshape(Bsz, T).to(torch.long).contiguous()
+        trg = trg.reshape(Bsz, T).to(torch.long).contiguous()
+        table = table.contiguous()
+        dev = logits.device
+        col_lse = torch.empty((Bsz, V), dtype=torch.float32, device=dev)
+        row_lse = torch.empty((Bsz, T), dtype=torch.float32, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        ws = torch.empty(lib().mamba_filtered_ce_workspace_bytes(Bsz, T, V), dtype=torch.uint8, device=dev)
+        a = _loss_args(logits, src, trg, table, boundaries, col_lse, row_lse, ws)
+        a.loss = _p(loss)
+        _call("mamba_filtered_ce_fwd", a, dev)
+        ctx.save_for_backward(logits, src, trg, table, col_lse, row_lse)
+        ctx.boundaries = tuple(int(b) for b in boundaries)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        logits, src, trg, table, col_lse, row_lse = ctx.saved_tensors
+        Bsz, T, V = logits.shape
+        dev = logits.device
+        # same strides as the logits: a padded LM-head output gets a padded gradient (pad columns zeroed once)
+        if logits.stride(1) != V or logits.stride(0) != T * V:
+            base = torch.zeros((Bsz, T, logits.stride(1)), dtype=logits.dtype, device=dev)
+            dlogits = base[:, :, :V]
+        else:
+            dlogits = torch.empty((Bsz, T, V), dtype=logits.dtype, device=dev)
+        ws = torch.empty(lib().mamba_filtered_ce_workspace_bytes(Bsz, T, V), dtype=torch.uint8, device=dev)
+        go = grad_out.to(torch.float32).contiguous()
+        a = _loss_args(logits, src, trg, table, ctx.boundaries, col_lse, row_lse, ws)
+        a.grad_out = _p(go)
+        a.dlogits, a.dlogits_bs, a.dlogits_ts = _p(dlogits), dlogits.stride(0), dlogits.stride(1)
+        _call("mamba_filtered_ce_bwd", a, dev)
+        return dlogits, None, None, None, None
+
+
+def filtered_ce_fn(logits, src, trg, table, boundaries):
+    """mean cross-entropy of the grammar-masked, sequence-normalised logits (see csrc/loss.cu)."""
+    return FilteredCEFn.apply(logits, src, trg, table, tuple(boundaries))
 
 
 # ------------------------------------------------------------------------------------------------

@@ -93,9 +93,19 @@ def filtered_logit(input, output):  # train.py:133-138
     return -log_probs * weights
 
 
-def loss_fn(src, trg, output):  # train.py:161-165
+def loss_fn_torch(src, trg, output):
+    """train.py:161-165 spelled with torch ops, as the reference does (about ten passes over [B, T, V])."""
     filtered_output = filtered_logit(src, output).reshape(-1, cc.vocab_size)
     return F.cross_entropy(filtered_output, trg.reshape(-1))
+
+
+def loss_fn(src, trg, output):
+    """train.py:161-165 (filtered_logit + CrossEntropyLoss) as one fused CUDA op: four streaming passes over the
+    logits in their storage dtype, deterministic.  CUDA only."""
+    from . import ops
+    s = cc.start_idx
+    boundaries = (s["dyn"] - 1, s["length"] - 1, s["time"] - 1, s["tempo"] - 1)
+    return ops.filtered_ce_fn(output, src, trg, make_distributions(output.device), boundaries)
 
 
 def train_step(model, optimizer, src, trg, meta, autocast_dtype=None):

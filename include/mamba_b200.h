@@ -249,6 +249,40 @@ int mamba_rmsnorm_fwd(const MambaNormArgs* args, void* stream);
 int mamba_rmsnorm_bwd(const MambaNormArgs* args, void* stream);
 size_t mamba_rmsnorm_bwd_workspace_bytes(int64_t rows, int dim);
 
+/* ------------------------------------------------------------------------------------------
+ * Grammar-masked loss.  Replaces train.py:133-138 (filtered_logit: weights picked by the bucket of the
+ * PREVIOUS token from a [5, V] table, log_softmax over dim=1 — the SEQUENCE axis —, f = -log_probs *
+ * weights) and train.py:161-165 (CrossEntropyLoss over the vocab axis, mean over B*T):
+ *     loss = mean_{b,t} [ logsumexp_v f[b,t,:] - f[b,t,trg[b,t]] ]
+ * `boundaries` are the 4 bucket edges of train.py:117-121 (bucketize, right=False); `table` is the
+ * [5, vocab] fp32 tensor of train.make_distributions (train.py:79-111).  logits: [B, T, V] in `dtype`,
+ * vocab axis contiguous, batch / time strides in elements (the padded LM-head output is consumed in
+ * place).  The forward writes loss[1], col_lse[B, V] and row_lse[B, T] (fp32; both are inputs of the
+ * backward).  The backward writes dlogits = d(loss * grad_out[0]) / d logits in `dtype`.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct MambaLossArgs {
+  int32_t struct_size;
+  int32_t dtype;
+  int32_t batch, seqlen, vocab;
+  int32_t boundaries[4];
+  int32_t reserved;
+  const void* logits;  int64_t logits_bs, logits_ts;
+  const int64_t* src;   /* [B, T] int64, contiguous */
+  const int64_t* trg;   /* [B, T] int64, contiguous */
+  const float* table;   /* [5, V] fp32              */
+  float* col_lse;       /* [B, V] fp32              */
+  float* row_lse;       /* [B, T] fp32              */
+  float* loss;          /* [1] fp32 (forward)       */
+  const float* grad_out; /* [1] fp32 device scalar or NULL (= 1)  (backward) */
+  void* dlogits;       int64_t dlogits_bs, dlogits_ts;  /* [B, T, V] dtype (backward) */
+  void* workspace;
+  size_t workspace_bytes; /* >= mamba_filtered_ce_workspace_bytes(); the forward's contents are not needed by the backward */
+} MambaLossArgs;
+
+int mamba_filtered_ce_fwd(const MambaLossArgs* args, void* stream);
+int mamba_filtered_ce_bwd(const MambaLossArgs* args, void* stream);
+size_t mamba_filtered_ce_workspace_bytes(int batch, int seqlen, int vocab);
+
 /* ------------------------------------------------------------------------------------------ */
 int mamba_abi_version(void);
 const char* mamba_last_error(void);

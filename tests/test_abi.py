@@ -37,7 +37,8 @@ def test_ctypes_struct_layout_matches_c(tmp_path):
     """Compile a C program against the header and compare sizeof/offsetof with the ctypes mirrors."""
     from mamba_b200 import _lib
     structs = {"MambaScanFwdArgs": _lib.ScanFwdArgs, "MambaScanBwdArgs": _lib.ScanBwdArgs,
-               "MambaConvArgs": _lib.ConvArgs, "MambaStepArgs": _lib.StepArgs, "MambaNormArgs": _lib.NormArgs}
+               "MambaConvArgs": _lib.ConvArgs, "MambaStepArgs": _lib.StepArgs, "MambaNormArgs": _lib.NormArgs,
+               "MambaLossArgs": _lib.LossArgs}
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void){"]
     for cname, ct in structs.items():
         lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')

@@ -196,3 +196,37 @@ def test_trainer_graph_step_equals_eager_step():
         assert abs(la.item() - lb.item()) <= 2e-4 * abs(la.item()), (i, la.item(), lb.item())
     for (n1, p1), (n2, p2) in zip(a.named_parameters(), b.named_parameters()):
         assert_close(p2, p1, 1e-3, 1e-4, what=f"param {n1} after 4 steps")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("padded", [False, True])
+def test_fused_loss_matches_oracle_loss(dtype, padded):
+    """ops.filtered_ce_fn (csrc/loss.cu) against the oracle's train.py:133-138 + :161-165, value and gradient; also
+    through a row-padded logits view (the LM head's layout)."""
+    from mamba_b200 import synthetic, train
+    from mamba_b200.configs import common as cc
+    V = cc.vocab_size
+    torch.manual_seed(0)
+    src, trg, _ = synthetic.batch(2, 150, seed=9)
+    base = torch.randn(2, 150, V + 6) * 2.0
+    x = base.to(dtype)
+    xr = x[..., :V].float().clone().requires_grad_(True)
+    loss_r = train_ref.loss_fn(src, trg, xr)
+    (loss_r * 1.7).backward()
+    if padded:
+        xg_base = x.cuda().requires_grad_(True)
+        xg = xg_base[..., :V]
+    else:
+        xg_base = x[..., :V].contiguous().cuda().requires_grad_(True)
+        xg = xg_base
+    loss_g = train.loss_fn(src.cuda(), trg.cuda(), xg)
+    (loss_g * 1.7).backward()
+    assert abs(loss_g.item() - loss_r.item()) <= 1e-4 * abs(loss_r.item()), (loss_g.item(), loss_r.item())
+    got = xg_base.grad[..., :V]
+    if dtype == torch.float32:
+        assert_close(got, xr.grad, 1e-4, 1e-5, what="loss dlogits fp32")
+    else:
+        assert_close(got, xr.grad, 2e-2, 2e-2, what="loss dlogits bf16")
+    # torch-op spelling of the same loss on the GPU (the drop-in mirror of the reference functions)
+    loss_t = train.loss_fn_torch(src.cuda(), trg.cuda(), xg.detach().float())
+    assert abs(loss_t.item() - loss_r.item()) <= 1e-4 * abs(loss_r.item())

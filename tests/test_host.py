@@ -28,7 +28,7 @@ def test_loss_path_matches_oracle_on_cpu():
     assert torch.equal(train.make_distributions("cpu"), train_ref.make_distributions())
     assert torch.equal(train.pick_distributions_by_prev_token(src), train_ref.pick_distributions_by_prev_token(src))
     assert torch.equal(train.filtered_logit(src, out), train_ref.filtered_logit(src, out))
-    assert torch.equal(train.loss_fn(src, trg, out), train_ref.loss_fn(src, trg, out))
+    assert torch.equal(train.loss_fn_torch(src, trg, out), train_ref.loss_fn(src, trg, out))
 
 
 def test_synthetic_batch_follows_grammar():
