@@ -389,3 +389,15 @@ def test_conv_and_ssm_step_match_oracle_recurrence(cfg):
         assert_close(y, y_ref, RTOL32, what=f"ssm_step y t={t}")
         assert_close(h_g, h_ref, RTOL32, what=f"ssm_step h t={t}")
         assert torch.equal(conv_g.cpu(), conv_ref)
+
+
+# ---------------------------------------------------------------------------------------------------
+# golden fixtures produced by the reference itself (tests/golden/make_golden.py)
+# ---------------------------------------------------------------------------------------------------
+def test_scan_kernel_matches_reference_golden_vector():
+    from pathlib import Path
+    from mamba_b200 import ops
+    f = torch.load(Path(__file__).resolve().parent / "golden" / "scan_small.pt")
+    g = {k: v.cuda() for k, v in f.items()}
+    y = ops.selective_scan_fn(g["u"], g["delta"], g["A"], g["B"], g["C"], g["D"])
+    assert_close(y, f["y"], RTOL32, what="CUDA scan vs reference golden")
