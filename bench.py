@@ -311,6 +311,15 @@ def main():
         "loss": loss_dev,
     }
 
+    if world > 1:
+        # Every collective of the run is behind us.  Ranks > 0 leave now; rank 0 goes on with rank-local
+        # measurements.  (No destroy_process_group: tearing NCCL down under a live CUDA graph that holds captured
+        # all-reduces can hang; the processes exit instead.)
+        dist.barrier()
+        torch.cuda.synchronize()
+        if rank != 0:
+            sys.stdout.flush()
+            os._exit(0)
     if rank == 0:
         # ---- roofline of the dominant kernel, timed live ------------------------------------------------
         try:
@@ -345,8 +354,9 @@ def main():
                                     "ms_per_step": ms}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
     return 0
 
 

@@ -119,6 +119,43 @@ def train_step(model, optimizer, src, trg, meta, autocast_dtype=None):
     return loss
 
 
+class FlatGrads:
+    """All gradients of a model in ONE flat fp32 buffer (every p.grad is a view into it), exchanged as a few large
+    buckets.  Data-parallel semantics of train_parallel.py:151 (DDP: gradient mean over ranks): each bucket is
+    pre-scaled by 1/world and sum-all-reduced, which is what DDP's default hook does and works on NCCL and gloo."""
+
+    def __init__(self, params, bucket_mb=64):
+        self.params = [p for p in params if p.requires_grad]
+        total = sum(p.numel() for p in self.params)
+        dev = self.params[0].device
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        off = 0
+        for p in self.params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        per = max(1, int(bucket_mb * (1 << 20) // 4))
+        self.buckets = [self.flat[i:i + per] for i in range(0, total, per)]
+
+    def zero(self):
+        self.flat.zero_()
+
+    def allreduce_mean(self, world_size, group=None):
+        if world_size <= 1:
+            return
+        import torch.distributed as dist
+        for b in self.buckets:
+            b.mul_(1.0 / world_size)
+            dist.all_reduce(b, op=dist.ReduceOp.SUM, group=group)
+
+
+def shard_rows(n_rows, rank, world_size):
+    """Contiguous shard [lo, hi) of `n_rows` independent sequences for `rank` (batch-sharded generation: the
+    sequences never exchange anything, so there is no collective on this path)."""
+    base, rem = divmod(n_rows, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
 class Trainer:
     """The reference's training step as ONE CUDA graph per rank.
 
@@ -150,24 +187,12 @@ class Trainer:
         self.use_graph = use_graph
         self.graph = None
 
-    # one flat fp32 gradient buffer; every p.grad is a view into it
     def _flatten_grads(self, bucket_mb):
-        params = [p for p in self.model.parameters() if p.requires_grad]
-        total = sum(p.numel() for p in params)
-        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=self.device)
-        off = 0
-        for p in params:
-            p.grad = self.flat_grad[off:off + p.numel()].view_as(p)
-            off += p.numel()
-        per = max(1, int(bucket_mb * (1 << 20) // 4))
-        self.buckets = [self.flat_grad[i:i + per] for i in range(0, total, per)]
+        self.grads = FlatGrads(self.model.parameters(), bucket_mb)
+        self.flat_grad = self.grads.flat
 
     def _allreduce(self):
-        if self.world_size <= 1:
-            return
-        import torch.distributed as dist
-        for b in self.buckets:
-            dist.all_reduce(b, op=dist.ReduceOp.AVG, group=self.pg)
+        self.grads.allreduce_mean(self.world_size, self.pg)
 
     def _step_body(self):
         with torch.autocast("cuda", dtype=self.autocast_dtype, enabled=self.autocast_dtype is not None):
