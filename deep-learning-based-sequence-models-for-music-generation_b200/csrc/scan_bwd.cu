@@ -27,14 +27,13 @@
 namespace mb {
 
 constexpr int kBD = 32;        // channels per CTA
-constexpr int kCK = 16;        // timesteps per chunk (= checkpoint interval of scan_fwd)
 constexpr int kBHelperWarps = 4;
 constexpr int kBHelperThreads = kBHelperWarps * 32;
 constexpr int kBMaxWarps = 8;  // scan warps per CTA
 constexpr int kBRing = 2;      // raw-tile ring depth (a chunk is >= 2 us of work at d_state 64)
 
 struct ScanBwdParams {
-  int B, L, D, N, NW, NPT, nck, flags, ntiles;
+  int B, L, D, N, NW, NPT, nck, ck, flags, ntiles;
   const void *u, *delta, *Bm, *Cm, *z, *dout, *ypre;
   int64_t u_bs, u_ls, delta_bs, delta_ls, B_bs, B_ls, C_bs, C_ls, z_bs, z_ls, dout_bs, dout_ls, ypre_bs, ypre_ls;
   void *du, *ddelta, *dz, *dB, *dC;
@@ -75,13 +74,31 @@ __device__ __forceinline__ void sts_vec(float* dst, const float (&v)[NPER]) {
 __device__ __forceinline__ float2 shfl_xor2(float2 v, int m) {
   return make_float2(__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m));
 }
+// One reduce-scatter step over the lane pair (lane, lane ^ MASK): on entry every lane holds CNT partial values
+// v[0..CNT); on exit v[0..CNT/2) holds the pair-sums of the lower half on lanes with the MASK bit clear and of the
+// upper half on lanes with it set.  CNT/2 shuffles instead of CNT (the selects run on the idle ALU pipe); the
+// shuffle/shared-memory pipe is the scarce one in this kernel.  With CNT == 1 it is a plain butterfly step.
+template <int CNT, int MASK>
+__device__ __forceinline__ void reduce_scatter_step(float (&v)[8], bool hi) {
+  if constexpr (CNT >= 2) {
+    constexpr int H = CNT / 2;
+#pragma unroll
+    for (int i = 0; i < H; ++i) {
+      const float send = hi ? v[i] : v[i + H];
+      const float keep = hi ? v[i + H] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, MASK);
+    }
+  } else {
+    v[0] += __shfl_xor_sync(0xffffffffu, v[0], MASK);
+  }
+}
 
 // Shared-memory layout.
 //   RAW ring slot (cp.async targets, element type T): u, delta, z, dout, ypre [CK][32];  B, C [CK][NPT]
 //   WORK slot (two): wdl, wdu, wdy fp32 [CK][32];  (bf16 I/O only) Bf, Cf fp32 [CK][NPT];
 //                    pg, pS [NW][CK][32] (per-warp partial sums over states);  redB, redC [CK][NPT]
-//   hs: float4 [CK][NPER][scan threads]  (h_t of the chunk, 4 channels per float4, thread-private)
-template <typename T>
+//   hs: float4 [CK/2][NPER][scan threads]  (h_t of the even steps of the chunk, 4 channels per float4, thread-private)
+template <typename T, int kCK>
 struct BwdLayout {
   int raw_u, raw_dl, raw_z, raw_do, raw_yp, raw_B, raw_C, raw_bytes;
   int w_dl, w_du, w_dy, w_Bf, w_Cf, w_pg, w_pS, w_rB, w_rC, work_bytes;
@@ -107,11 +124,11 @@ struct BwdLayout {
     w_rB = o, o += kCK * NPT * 4;
     w_rC = o, o += kCK * NPT * 4;
     work_bytes = (o + 127) & ~127;
-    hs_bytes = kCK * NPER * NW * 32 * 16;
+    hs_bytes = (kCK / 2) * NPER * NW * 32 * 16;  // even steps only
   }
 };
 
-template <typename T, int NPER, int NW>
+template <typename T, int NPER, int NW, int kCK>
 __global__ void __launch_bounds__((NW + kBHelperWarps) * 32, 1) scan_bwd_kernel(const ScanBwdParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -119,7 +136,7 @@ __global__ void __launch_bounds__((NW + kBHelperWarps) * 32, 1) scan_bwd_kernel(
   const int b = blockIdx.y, tile = blockIdx.x;
   const int d0 = tile * kBD;
   const int dvalid = min(kBD, p.D - d0);
-  const BwdLayout<T> lay(NW, NPT, NPER);
+  const BwdLayout<T, kCK> lay(NW, NPT, NPER);
   unsigned char* const raw_base = smem;
   unsigned char* const work_base = smem + (size_t)kBRing * lay.raw_bytes;
   float4* const hs = reinterpret_cast<float4*>(work_base + (size_t)2 * lay.work_bytes);
@@ -212,15 +229,17 @@ __global__ void __launch_bounds__((NW + kBHelperWarps) * 32, 1) scan_bwd_kernel(
             const float2 a = make_float2(ex2_approx(g.x), ex2_approx(g.y));
             h[q][j] = __ffma2_rn(a, h[q][j], __fmul2_rn(dup[q], Bb));
           }
-          hst[(t * NPER + j) * nscan_threads] = make_float4(h[0][j].x, h[0][j].y, h[1][j].x, h[1][j].y);
+          if ((t & 1) == 0)  // odd steps are rebuilt in the reverse sweep from the even one before them
+            hst[((t >> 1) * NPER + j) * nscan_threads] = make_float4(h[0][j].x, h[0][j].y, h[1][j].x, h[1][j].y);
         }
       }
       // prefetch the next chunk's start state: its latency hides behind the reverse sweep
       if (c > 0) load_ckpt(c - 1, hnext);
 
       // ---- reverse sweep: adjoint recurrence ------------------------------------------------------------------
-#pragma unroll 2
-      for (int t = kCK - 1; t >= 0; --t) {
+      // Steps are taken in (odd, even) pairs: only h of the even step is in shared memory; the odd step's state
+      // is h_odd = a_odd * h_even + delta*u*B, whose first term is exactly the a_t * h_{t-1} the gradient needs.
+      auto rev_step = [&](const int t, const float2 (&hprev)[2][NPER], const bool odd) {
         const float4 dl4 = *reinterpret_cast<const float4*>(wdl + t * kBD);
         const float4 du4 = *reinterpret_cast<const float4*>(wdu + t * kBD);
         const float4 dy4 = *reinterpret_cast<const float4*>(wdy + t * kBD);
@@ -232,56 +251,72 @@ __global__ void __launch_bounds__((NW + kBHelperWarps) * 32, 1) scan_bwd_kernel(
         lds_vec<NPER>(Cv, Cf + t * NPT);
         float2 gs[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
         float2 S[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
-        float2 bc[NPER];  // (dB, dC) partial of this thread's 4 channels, per state
+        float red[8];  // (dB_j, dC_j) partials of this thread's 4 channels, j = 0..NPER-1
 #pragma unroll
         for (int j = 0; j < NPER; ++j) {
-          const float4 hc4 = hst[(t * NPER + j) * nscan_threads];
-          const float2 hc[2] = {make_float2(hc4.x, hc4.y), make_float2(hc4.z, hc4.w)};
           const float2 Bb = make_float2(Bv[j], Bv[j]), Cb = make_float2(Cv[j], Cv[j]);
           float2 db2 = make_float2(0.f, 0.f), dc2 = make_float2(0.f, 0.f);
 #pragma unroll
           for (int q = 0; q < 2; ++q) {
             const float2 ga = __fmul2_rn(dlp[q], A2[q][j]);
             const float2 a = make_float2(ex2_approx(ga.x), ex2_approx(ga.y));
+            const float2 bu = __fmul2_rn(dup[q], Bb);
+            float2 hm, hc;  // hm = a_t * h_{t-1}, hc = h_t
+            if (odd) {
+              hm = __fmul2_rn(a, hprev[q][j]);
+              hc = __fadd2_rn(hm, bu);
+            } else {
+              hc = hprev[q][j];
+              hm = __ffma2_rn(make_float2(-dup[q].x, -dup[q].y), Bb, hc);
+            }
             const float2 dh = __ffma2_rn(Cb, dyp[q], dhc[q][j]);
-            dc2 = __ffma2_rn(dyp[q], hc[q], dc2);
-            const float2 ndu = make_float2(-dup[q].x, -dup[q].y);
-            const float2 hm = __ffma2_rn(ndu, Bb, hc[q]);  // a_t * h_{t-1} = h_t - delta*u*B
-            const float2 g = __fmul2_rn(dh, hm);            // dL/d(delta*A) for these two (d, n)
+            dc2 = __ffma2_rn(dyp[q], hc, dc2);
+            const float2 g = __fmul2_rn(dh, hm);  // dL/d(delta*A) for these two (d, n)
             gs[q] = __ffma2_rn(g, A2[q][j], gs[q]);
             dAacc[q][j] = __ffma2_rn(g, dlp[q], dAacc[q][j]);
             S[q] = __ffma2_rn(dh, Bb, S[q]);
             db2 = __ffma2_rn(dh, dup[q], db2);
             dhc[q][j] = __fmul2_rn(a, dh);
           }
-          bc[j] = make_float2(db2.x + db2.y, dc2.x + dc2.y);
+          red[2 * j] = db2.x + db2.y, red[2 * j + 1] = dc2.x + dc2.y;
         }
-        // sums over this warp's state-lanes (lane bits 3, 4), then one partial per warp
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          gs[q] = __fadd2_rn(gs[q], shfl_xor2(gs[q], 8));
-          S[q] = __fadd2_rn(S[q], shfl_xor2(S[q], 8));
-          gs[q] = __fadd2_rn(gs[q], shfl_xor2(gs[q], 16));
-          S[q] = __fadd2_rn(S[q], shfl_xor2(S[q], 16));
+        // sums over this warp's 4 state-lanes (lane bits 4, 3): reduce-scatter of the 8 values
+        // (g of 4 channels, S of 4 channels); every lane ends up with 2 of them
+        {
+          float v[8] = {gs[0].x, gs[0].y, gs[1].x, gs[1].y, S[0].x, S[0].y, S[1].x, S[1].y};
+          reduce_scatter_step<8, 16>(v, lane & 16);
+          reduce_scatter_step<4, 8>(v, lane & 8);
+          float* dst = ((lane & 16) ? pS : pg) + t * kBD + ((lane & 8) ? 2 : 0);
+          *reinterpret_cast<float2*>(dst) = make_float2(v[0], v[1]);
         }
-        if (ln == 0) {
-          *reinterpret_cast<float4*>(pg + t * kBD) = make_float4(gs[0].x, gs[0].y, gs[1].x, gs[1].y);
-          *reinterpret_cast<float4*>(pS + t * kBD) = make_float4(S[0].x, S[0].y, S[1].x, S[1].y);
+        // sums over the warp's 8 channel-lanes (lane bits 2, 1, 0): reduce-scatter of the 2*NPER values
+        {
+          reduce_scatter_step<2 * NPER, 4>(red, lane & 4);
+          reduce_scatter_step<(NPER >= 2 ? NPER : 1), 2>(red, lane & 2);
+          reduce_scatter_step<(NPER >= 4 ? NPER / 2 : 1), 1>(red, lane & 1);
+          // lane (b2 b1 b0) now holds value index idx of the original (dB_0, dC_0, dB_1, dC_1, ...) list
+          int idx;
+          bool writer = true;
+          if constexpr (NPER == 4) {
+            idx = lane & 7;
+          } else if constexpr (NPER == 2) {
+            idx = (lane >> 1) & 3, writer = (lane & 1) == 0;
+          } else {
+            idx = (lane >> 2) & 1, writer = (lane & 3) == 0;
+          }
+          if (writer) ((idx & 1) ? redC : redB)[t * NPT + (idx >> 1)] = red[0];
         }
-        // sums over the warp's channel-lanes (lane bits 0..2)
+      };
+#pragma unroll 1
+      for (int tp = kCK / 2 - 1; tp >= 0; --tp) {
+        float2 he[2][NPER];
 #pragma unroll
         for (int j = 0; j < NPER; ++j) {
-          bc[j] = __fadd2_rn(bc[j], shfl_xor2(bc[j], 1));
-          bc[j] = __fadd2_rn(bc[j], shfl_xor2(bc[j], 2));
-          bc[j] = __fadd2_rn(bc[j], shfl_xor2(bc[j], 4));
+          const float4 h4 = hst[(tp * NPER + j) * nscan_threads];
+          he[0][j] = make_float2(h4.x, h4.y), he[1][j] = make_float2(h4.z, h4.w);
         }
-        if (ld == 0) {
-          float vb[NPER], vc[NPER];
-#pragma unroll
-          for (int j = 0; j < NPER; ++j) vb[j] = bc[j].x, vc[j] = bc[j].y;
-          sts_vec<NPER>(redB + t * NPT, vb);
-          sts_vec<NPER>(redC + t * NPT, vc);
-        }
+        rev_step(2 * tp + 1, he, true);
+        rev_step(2 * tp, he, false);
       }
       bar_arrive(3 + ws, bar_count);  // chunk c swept
       rslot = (rslot + 1 == kBRing) ? 0 : rslot + 1;
@@ -305,6 +340,7 @@ __global__ void __launch_bounds__((NW + kBHelperWarps) * 32, 1) scan_bwd_kernel(
   const int ht = tid - nscan_threads;  // 0..127
   const bool do_softplus = p.flags & MAMBA_FLAG_DELTA_SOFTPLUS;
   const int my_t = ht >> 3, my_c = 4 * (ht & 7);  // this thread's (timestep, 4 channels) of every chunk
+  const bool my_row = my_t < kCK;                  // with 8-step chunks half of the helper threads only load
   float bias4[4], D4[4], dD_acc[4], db_acc[4];
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
@@ -353,6 +389,7 @@ __global__ void __launch_bounds__((NW + kBHelperWarps) * 32, 1) scan_bwd_kernel(
     unsigned char* wbase = work_base + (size_t)(it & 1) * lay.work_bytes;
     const int rv = min(kCK, p.L - c * kCK);
     const int o = my_t * kBD + my_c;
+    if (my_row) {
     float dl[4], uu[4], dy[4], du[4];
     V4<T>::ld(reinterpret_cast<const T*>(rbase + lay.raw_dl) + o, dl);
     V4<T>::ld(reinterpret_cast<const T*>(rbase + lay.raw_u) + o, uu);
@@ -373,6 +410,7 @@ __global__ void __launch_bounds__((NW + kBHelperWarps) * 32, 1) scan_bwd_kernel(
     *reinterpret_cast<float4*>(reinterpret_cast<float*>(wbase + lay.w_dl) + o) = make_float4(dl[0], dl[1], dl[2], dl[3]);
     *reinterpret_cast<float4*>(reinterpret_cast<float*>(wbase + lay.w_du) + o) = make_float4(du[0], du[1], du[2], du[3]);
     *reinterpret_cast<float4*>(reinterpret_cast<float*>(wbase + lay.w_dy) + o) = make_float4(dy[0], dy[1], dy[2], dy[3]);
+    }
     if (sizeof(T) != 4) {
       const T* sB = reinterpret_cast<const T*>(rbase + lay.raw_B);
       const T* sC = reinterpret_cast<const T*>(rbase + lay.raw_C);
@@ -402,7 +440,7 @@ __global__ void __launch_bounds__((NW + kBHelperWarps) * 32, 1) scan_bwd_kernel(
     unsigned char* wbase = work_base + (size_t)(it & 1) * lay.work_bytes;
     const int t0 = c * kCK;
     const int rv = min(kCK, p.L - t0);
-    if (my_t < rv) {
+    if (my_row && my_t < rv) {
       const int o = my_t * kBD + my_c;
       const float* pg = reinterpret_cast<const float*>(wbase + lay.w_pg) + o;
       const float* pS = reinterpret_cast<const float*>(wbase + lay.w_pS) + o;
@@ -493,14 +531,15 @@ __global__ void __launch_bounds__((NW + kBHelperWarps) * 32, 1) scan_bwd_kernel(
   // ---- dD / d_bias: sum this CTA's 16 timestep-rows in shared memory, one partial per (b, d) ------------------
   bar_sync(5, kBHelperThreads);
   float* fin = reinterpret_cast<float*>(work_base);  // [2][16][32], the work slots are free now
+  constexpr int kRows = kBHelperThreads / 8;
   *reinterpret_cast<float4*>(fin + my_t * kBD + my_c) = make_float4(dD_acc[0], dD_acc[1], dD_acc[2], dD_acc[3]);
-  *reinterpret_cast<float4*>(fin + (kCK + my_t) * kBD + my_c) = make_float4(db_acc[0], db_acc[1], db_acc[2], db_acc[3]);
+  *reinterpret_cast<float4*>(fin + (kRows + my_t) * kBD + my_c) = make_float4(db_acc[0], db_acc[1], db_acc[2], db_acc[3]);
   bar_sync(5, kBHelperThreads);
   if (ht < kBD && d0 + ht < p.D) {
     float sD = 0.f, sb = 0.f;
-    for (int r = 0; r < kCK; ++r) {
+    for (int r = 0; r < kRows; ++r) {
       sD += fin[r * kBD + ht];
-      sb += fin[(kCK + r) * kBD + ht];
+      sb += fin[(kRows + r) * kBD + ht];
     }
     p.ws_dD[(int64_t)b * p.D + d0 + ht] = sD;
     p.ws_db[(int64_t)b * p.D + d0 + ht] = sb;
@@ -555,9 +594,9 @@ __global__ void scan_bwd_finalize_kernel(const ScanBwdParams p, int rows_per_blo
   }
 }
 
-template <typename T>
+template <typename T, int kCK>
 static size_t bwd_smem_bytes(int NW, int NPT, int NPER) {
-  const BwdLayout<T> lay(NW, NPT, NPER);
+  const BwdLayout<T, kCK> lay(NW, NPT, NPER);
   return (size_t)kBRing * lay.raw_bytes + (size_t)2 * lay.work_bytes + lay.hs_bytes;
 }
 
@@ -575,12 +614,12 @@ static size_t bwd_workspace_layout(int B, int L, int D, int N, size_t* o_dB, siz
   return off;
 }
 
-template <typename T, int NPER, int NW>
+template <typename T, int NPER, int NW, int kCK>
 static int launch_bwd(const ScanBwdParams& p, cudaStream_t stream) {
-  const size_t smem = bwd_smem_bytes<T>(NW, p.NPT, NPER);
+  const size_t smem = bwd_smem_bytes<T, kCK>(NW, p.NPT, NPER);
   if (smem > 227 * 1024)
     return set_error(MAMBA_ESIZE, "scan_bwd: d_state %d needs %zu B of shared memory", p.N, smem);
-  auto kern = scan_bwd_kernel<T, NPER, NW>;
+  auto kern = scan_bwd_kernel<T, NPER, NW, kCK>;
   static thread_local size_t configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -600,15 +639,20 @@ static int launch_bwd(const ScanBwdParams& p, cudaStream_t stream) {
   return check_launch("scan_bwd_finalize");
 }
 
-template <typename T, int NPER>
+template <typename T, int NPER, int kCK>
 static int bwd_dispatch_nw(const ScanBwdParams& p, cudaStream_t stream) {
   switch (p.NW) {
-    case 1: return launch_bwd<T, NPER, 1>(p, stream);
-    case 2: return launch_bwd<T, NPER, 2>(p, stream);
-    case 3: case 4: return launch_bwd<T, NPER, 4>(p, stream);
-    case 5: case 6: case 7: case 8: return launch_bwd<T, NPER, 8>(p, stream);
+    case 1: return launch_bwd<T, NPER, 1, kCK>(p, stream);
+    case 2: return launch_bwd<T, NPER, 2, kCK>(p, stream);
+    case 4: return launch_bwd<T, NPER, 4, kCK>(p, stream);
+    case 8: return launch_bwd<T, NPER, 8, kCK>(p, stream);
   }
   return set_error(MAMBA_ESIZE, "scan_bwd: d_state %d too large (max %d)", p.N, kBMaxWarps * 16);
+}
+
+template <typename T, int NPER>
+static int bwd_dispatch_ck(const ScanBwdParams& p, cudaStream_t stream) {
+  return p.ck == 8 ? bwd_dispatch_nw<T, NPER, 8>(p, stream) : bwd_dispatch_nw<T, NPER, 16>(p, stream);
 }
 
 template <typename T>
@@ -618,9 +662,9 @@ static int bwd_dispatch(ScanBwdParams& p, int nper, cudaStream_t stream) {
   p.NW = p.NW <= 2 ? p.NW : (p.NW <= 4 ? 4 : 8);  // instantiated warp counts
   p.NPT = (p.NW * 4 * nper + 7) & ~7;
   switch (nper) {
-    case 1: return bwd_dispatch_nw<T, 1>(p, stream);
-    case 2: return bwd_dispatch_nw<T, 2>(p, stream);
-    case 4: return bwd_dispatch_nw<T, 4>(p, stream);
+    case 1: return bwd_dispatch_ck<T, 1>(p, stream);
+    case 2: return bwd_dispatch_ck<T, 2>(p, stream);
+    case 4: return bwd_dispatch_ck<T, 4>(p, stream);
   }
   return set_error(MAMBA_EINVAL, "scan_bwd: variant must be 0, 1, 2 or 4 (got %d)", nper);
 }
@@ -647,7 +691,7 @@ extern "C" int mamba_scan_bwd(const MambaScanBwdArgs* a, void* stream) {
   if (a->batch > 65535) return set_error(MAMBA_ESIZE, "scan_bwd: batch %d above 65535", a->batch);
   if (!a->u || !a->delta || !a->A || !a->B || !a->C || !a->dout || !a->du || !a->ddelta || !a->dB || !a->dC || !a->dA)
     return set_error(MAMBA_EINVAL, "scan_bwd: null input or output pointer");
-  if (a->chunk != kCK) return set_error(MAMBA_EINVAL, "scan_bwd: chunk must be %d (got %d)", kCK, a->chunk);
+  if (a->chunk != 8 && a->chunk != 16) return set_error(MAMBA_EINVAL, "scan_bwd: chunk must be 8 or 16 (got %d)", a->chunk);
   if (a->seqlen > a->chunk && !a->ckpt) return set_error(MAMBA_EINVAL, "scan_bwd: ckpt == NULL");
   if ((a->flags & MAMBA_FLAG_HAS_Z) && (!a->z || !a->dz || !a->y_pre))
     return set_error(MAMBA_EINVAL, "scan_bwd: HAS_Z but z/dz/y_pre NULL");
@@ -658,7 +702,8 @@ extern "C" int mamba_scan_bwd(const MambaScanBwdArgs* a, void* stream) {
 
   ScanBwdParams p{};
   p.B = a->batch, p.L = a->seqlen, p.D = a->dim, p.N = a->dstate, p.flags = a->flags;
-  p.nck = ceil_div(p.L, kCK);
+  p.ck = a->chunk;
+  p.nck = ceil_div(p.L, p.ck);
   p.ntiles = ceil_div(p.D, kBD);
   p.u = a->u, p.delta = a->delta, p.Bm = a->B, p.Cm = a->C, p.z = a->z, p.dout = a->dout, p.ypre = a->y_pre;
   p.u_bs = a->u_bs, p.u_ls = a->u_ls, p.delta_bs = a->delta_bs, p.delta_ls = a->delta_ls;
@@ -695,7 +740,7 @@ extern "C" int mamba_scan_bwd(const MambaScanBwdArgs* a, void* stream) {
   p.vec_ck = a->ckpt && aligned16(a->ckpt) && (p.D % 4 == 0);
 
   int nper = a->variant;
-  if (nper == 0) nper = p.N <= 16 ? 1 : (p.N <= 32 ? 2 : 4);  // at most 4 scan warps: keeps the per-warp partials small
+  if (nper == 0) nper = p.N <= 16 ? 1 : (p.N <= 64 ? 2 : 4);  // measured: 8 scan warps of 4x2 tiles beat 4 of 4x4 at N = 64
   while (nper < 4 && ceil_div(p.N, 4 * nper) > kBMaxWarps) nper *= 2;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   return a->dtype == MAMBA_F32 ? bwd_dispatch<float>(p, nper, st) : bwd_dispatch<__nv_bfloat16>(p, nper, st);

@@ -32,7 +32,7 @@ constexpr int kMaxScanWarps = 16;
 constexpr int kMaxBCVec = 4;  // precomputed B/C cp.async slots per helper thread (fast path)
 
 struct ScanFwdParams {
-  int B, L, D, N, NS, NPT, nck, flags;
+  int B, L, D, N, NS, NPT, nck, cki, flags;
   const void *u, *delta, *Bm, *Cm, *z;
   void* out;
   int64_t u_bs, u_ls, delta_bs, delta_ls, B_bs, B_ls, C_bs, C_ls, z_bs, z_ls, out_bs, out_ls;
@@ -68,8 +68,9 @@ struct FwdLayout {
   }
 };
 
-template <typename T, int NPER, int RR>
+template <typename T, int NPER, int RR, int CKI>
 __global__ void __launch_bounds__((kMaxScanWarps + kHelperWarps) * 32) scan_fwd_kernel(const ScanFwdParams p) {
+  static_assert(kTS % CKI == 0, "a stage holds whole checkpoint chunks");
   static_assert(NPER % 4 == 0, "states per thread come in float4 groups");
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -142,13 +143,16 @@ __global__ void __launch_bounds__((kMaxScanWarps + kHelperWarps) * 32) scan_fwd_
         dd_cur = dd_nxt;
 #pragma unroll
         for (int q = 0; q < NPER / 4; ++q) Bc[q] = Bn[q], Cc[q] = Cn[q];
-      }
-      // h is now the state at the start of checkpoint chunk c + 1
-      if (p.ckpt != nullptr && (c + 1) * kTS < p.L && d < p.D) {
-        float* ck = p.ckpt + (((int64_t)b * p.nck + (c + 1)) * p.N + s * NPER) * p.D + d;
+        if ((t + 1) % CKI == 0) {
+          // h is now the state at the start of checkpoint chunk (c*kTS + t + 1) / CKI
+          const int tg_next = c * kTS + t + 1;
+          if (p.ckpt != nullptr && tg_next < p.L && d < p.D) {
+            float* ck = p.ckpt + (((int64_t)b * p.nck + tg_next / CKI) * p.N + s * NPER) * p.D + d;
 #pragma unroll
-        for (int j = 0; j < NPER; ++j)
-          if (s * NPER + j < p.N) ck[(int64_t)j * p.D] = (j & 1) ? h[j / 2].y : h[j / 2].x;
+            for (int j = 0; j < NPER; ++j)
+              if (s * NPER + j < p.N) ck[(int64_t)j * p.D] = (j & 1) ? h[j / 2].y : h[j / 2].x;
+          }
+        }
       }
       bar_arrive(3 + ws, bar_count);  // stage c scanned
       rslot = (rslot + 1 == RR) ? 0 : rslot + 1;
@@ -364,11 +368,11 @@ static size_t fwd_smem_bytes(int NS, int NPT, int RR) {
   return (size_t)RR * lay.raw_bytes + (size_t)2 * lay.work_bytes;
 }
 
-template <typename T, int NPER, int RR>
+template <typename T, int NPER, int RR, int CKI>
 static int launch_fwd(const ScanFwdParams& p, cudaStream_t stream) {
   const size_t smem = fwd_smem_bytes<T>(p.NS, p.NPT, RR);
   if (smem > 227 * 1024) return set_error(MAMBA_ESIZE, "scan_fwd: d_state %d needs %zu B of shared memory", p.N, smem);
-  auto kern = scan_fwd_kernel<T, NPER, RR>;
+  auto kern = scan_fwd_kernel<T, NPER, RR, CKI>;
   static thread_local size_t configured = 0;  // per instantiation: raise the dynamic-smem limit once per size
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -381,11 +385,16 @@ static int launch_fwd(const ScanFwdParams& p, cudaStream_t stream) {
   return check_launch("scan_fwd");
 }
 
-template <typename T, int NPER>
+template <typename T, int NPER, int CKI>
 static int dispatch_ring(const ScanFwdParams& p, cudaStream_t stream) {
   // deep ring when a stage is short (few states): bytes in flight must cover HBM latency with one CTA per SM
-  if (p.N <= 32 && fwd_smem_bytes<T>(p.NS, p.NPT, 8) <= 100 * 1024) return launch_fwd<T, NPER, 8>(p, stream);
-  return launch_fwd<T, NPER, 4>(p, stream);
+  if (p.N <= 32 && fwd_smem_bytes<T>(p.NS, p.NPT, 8) <= 100 * 1024) return launch_fwd<T, NPER, 8, CKI>(p, stream);
+  return launch_fwd<T, NPER, 4, CKI>(p, stream);
+}
+
+template <typename T, int NPER>
+static int dispatch_cki(const ScanFwdParams& p, cudaStream_t stream) {
+  return p.cki == 8 ? dispatch_ring<T, NPER, 8>(p, stream) : dispatch_ring<T, NPER, 16>(p, stream);
 }
 
 template <typename T>
@@ -395,9 +404,9 @@ static int dispatch_nper(ScanFwdParams& p, int nper, cudaStream_t stream) {
   p.NPT = (np + 7) & ~7;
   if (p.NS > kMaxScanWarps) return set_error(MAMBA_ESIZE, "scan_fwd: d_state %d too large for %d states/thread", p.N, nper);
   switch (nper) {
-    case 4: return dispatch_ring<T, 4>(p, stream);
-    case 8: return dispatch_ring<T, 8>(p, stream);
-    case 16: return dispatch_ring<T, 16>(p, stream);
+    case 4: return dispatch_cki<T, 4>(p, stream);
+    case 8: return dispatch_cki<T, 8>(p, stream);
+    case 16: return dispatch_cki<T, 16>(p, stream);
   }
   return set_error(MAMBA_EINVAL, "scan_fwd: variant must be 0, 4, 8 or 16 (got %d)", nper);
 }
@@ -428,12 +437,13 @@ extern "C" int mamba_scan_fwd(const MambaScanFwdArgs* a, void* stream) {
   if ((a->flags & MAMBA_FLAG_HAS_DELTA_BIAS) && !a->delta_bias)
     return set_error(MAMBA_EINVAL, "scan_fwd: HAS_DELTA_BIAS but delta_bias == NULL");
   if (a->dtype != MAMBA_F32 && a->dtype != MAMBA_BF16) return set_error(MAMBA_EDTYPE, "scan_fwd: dtype %d", a->dtype);
-  if (a->ckpt && a->chunk != kTS)
-    return set_error(MAMBA_EINVAL, "scan_fwd: chunk must be %d (got %d)", kTS, a->chunk);
+  if (a->ckpt && a->chunk != 8 && a->chunk != 16)
+    return set_error(MAMBA_EINVAL, "scan_fwd: chunk must be 8 or 16 (got %d)", a->chunk);
 
   ScanFwdParams p{};
   p.B = a->batch, p.L = a->seqlen, p.D = a->dim, p.N = a->dstate, p.flags = a->flags;
-  p.nck = ceil_div(p.L, kTS);
+  p.cki = a->ckpt ? a->chunk : 16;
+  p.nck = ceil_div(p.L, p.cki);
   p.u = a->u, p.delta = a->delta, p.Bm = a->B, p.Cm = a->C, p.z = a->z, p.out = a->out;
   p.u_bs = a->u_bs, p.u_ls = a->u_ls, p.delta_bs = a->delta_bs, p.delta_ls = a->delta_ls;
   p.B_bs = a->B_bs, p.B_ls = a->B_ls, p.C_bs = a->C_bs, p.C_ls = a->C_ls;

@@ -69,7 +69,7 @@ typedef struct MambaScanFwdArgs {
   int32_t struct_size; /* = sizeof(MambaScanFwdArgs) */
   int32_t dtype;
   int32_t batch, seqlen, dim, dstate;
-  int32_t chunk; /* checkpoint interval in timesteps: must be 16 (ignored if ckpt == NULL)  */
+  int32_t chunk; /* checkpoint interval in timesteps: 8 or 16 (ignored if ckpt == NULL)     */
   int32_t flags;
   int32_t variant; /* 0 = auto; otherwise states per thread (4, 8 or 16) — tuning knob */
   int32_t reserved;

@@ -44,6 +44,7 @@ SHAPES = [  # (B, L, D, N)
     (2, 257, 40, 8),      # D not a multiple of 32 (ragged channel tile), N = 8
     (1, 64, 32, 5),       # odd d_state
     (1, 130, 36, 48),     # D % 4 == 0 but % 32 != 0, N = 48
+    (2, 70, 64, 32),      # N = 32
 ]
 
 
@@ -102,7 +103,7 @@ def test_scan_forward_strided_views_and_softplus_threshold():
 
 
 @pytest.mark.parametrize("shape", SHAPES)
-@pytest.mark.parametrize("chunk", [16])
+@pytest.mark.parametrize("chunk", [8, 16])
 def test_scan_backward_fp32(shape, chunk):
     from mamba_b200 import ops
     B, L, D, N = shape
