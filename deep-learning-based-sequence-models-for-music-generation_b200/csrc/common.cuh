@@ -109,6 +109,22 @@ struct V4<__nv_bfloat16> {
 };
 
 
+
+// 8 consecutive bf16 -> 8 floats through one 16-byte shared load and two 16-byte shared stores
+__device__ __forceinline__ void cvt8_bf16_f32(const __nv_bfloat16* src, float* dst) {
+  const uint4 r = *reinterpret_cast<const uint4*>(src);
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+  float o[8];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    o[2 * k] = __uint_as_float(w[k] << 16);
+    o[2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u);
+  }
+  *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+  *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
+}
+__device__ __forceinline__ void cvt8_bf16_f32(const float*, float*) {}  // never called (fp32 tiles are read in place)
+
 // ---- async copies (LDGSTS) ----------------------------------------------------------------
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
   uint32_t s = (uint32_t)__cvta_generic_to_shared(smem_dst);

@@ -307,7 +307,7 @@ __global__ void __launch_bounds__((NW + kBHelperWarps) * 32, 1) scan_bwd_kernel(
           if (writer) ((idx & 1) ? redC : redB)[t * NPT + (idx >> 1)] = red[0];
         }
       };
-#pragma unroll 1
+#pragma unroll 2
       for (int tp = kCK / 2 - 1; tp >= 0; --tp) {
         float2 he[2][NPER];
 #pragma unroll
@@ -416,9 +416,9 @@ __global__ void __launch_bounds__((NW + kBHelperWarps) * 32, 1) scan_bwd_kernel(
       const T* sC = reinterpret_cast<const T*>(rbase + lay.raw_C);
       float* Bf = reinterpret_cast<float*>(wbase + lay.w_Bf);
       float* Cf = reinterpret_cast<float*>(wbase + lay.w_Cf);
-      for (int i = ht; i < kCK * NPT; i += kBHelperThreads) {
-        Bf[i] = IO<T>::cvt(sB[i]);
-        Cf[i] = IO<T>::cvt(sC[i]);
+      for (int i = ht; i < kCK * NPT / 8; i += kBHelperThreads) {  // NPT is a multiple of 8
+        cvt8_bf16_f32(sB + 8 * i, Bf + 8 * i);
+        cvt8_bf16_f32(sC + 8 * i, Cf + 8 * i);
       }
     }
   };

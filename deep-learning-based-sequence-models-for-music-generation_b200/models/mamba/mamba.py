@@ -141,20 +141,34 @@ class MambaBlock(nn.Module):  # simple_mamba @L184
         return conv_state, ssm_state
 
     @torch.no_grad()
-    def step(self, x_t, conv_state, ssm_state):
+    def step_constants(self):
+        """Per-layer tensors the decode step needs in kernel form (fp32, contiguous): built once per decode run
+        instead of once per token — A = -exp(A_log) alone is three launches."""
+        p = self.params
+        return dict(
+            conv_w=self.conv1d.weight.detach().float().reshape(p.d_inner, p.d_conv).contiguous(),
+            conv_b=None if self.conv1d.bias is None else self.conv1d.bias.detach().float().contiguous(),
+            dt_w=self.dt_proj.weight.detach().float().contiguous(),
+            dt_b=self.dt_proj.bias.detach().float().contiguous(),
+            A=(-torch.exp(self.A_log.detach().float())).contiguous(),
+            D=self.D.detach().float().contiguous())
+
+    @torch.no_grad()
+    def step(self, x_t, conv_state, ssm_state, consts=None):
         """One new position: x_t [B, d_model] -> [B, d_model]; both states are updated in place."""
         p = self.params
-        xz = self.in_proj(x_t)                                            # [B, 2*d_inner]
-        xs, res = xz.split([p.d_inner, p.d_inner], dim=-1)
-        w2 = self.conv1d.weight.detach().float().view(p.d_inner, p.d_conv)
-        cb = None if self.conv1d.bias is None else self.conv1d.bias.detach().float()
+        k = consts if consts is not None else self.step_constants()
         T = conv_state.dtype                                              # the step's activation dtype
-        xc = ops.conv_step(xs.to(T), conv_state, w2, cb)
-        A = -torch.exp(self.A_log.float())
-        x_dbl = self.x_proj(xc).to(T)
+        xz = self.in_proj(x_t)                                            # [B, 2*d_inner]
+        if xz.dtype != T:
+            xz = xz.to(T)
+        xs, res = xz.split([p.d_inner, p.d_inner], dim=-1)
+        xc = ops.conv_step(xs, conv_state, k["conv_w"], k["conv_b"])
+        x_dbl = self.x_proj(xc)
+        if x_dbl.dtype != T:
+            x_dbl = x_dbl.to(T)
         dt_r, Bv, Cv = x_dbl.split([p.dt_rank, p.d_state, p.d_state], dim=-1)
-        y = ops.ssm_step(xc, dt_r, Bv, Cv, self.dt_proj.weight.detach().float().contiguous(),
-                         self.dt_proj.bias.detach().float(), A, self.D.detach().float(), res.to(T), ssm_state)
+        y = ops.ssm_step(xc, dt_r, Bv, Cv, k["dt_w"], k["dt_b"], k["A"], k["D"], res, ssm_state)
         return self.out_proj(y)
 
 
@@ -177,6 +191,11 @@ def _params_from_configs(d_model=None, n_layers=None, vocab_size=None, pad=False
                      expand=mv.expand, d_conv=mv.d_conv, conv_bias=mv.conv_bias, bias=mv.bias,
                      pad_vocab_size_multiple=mv.pad_vocab_size_multiple if pad else 1,
                      metadata_vocab_size=cc.metadata_vocab_size)
+
+
+class InferenceCache(list):
+    """Per-layer (conv_state, ssm_state) pairs; also carries the per-layer step constants once they are built."""
+    consts = None
 
 
 class _PaddedHeadFn(torch.autograd.Function):
@@ -279,7 +298,7 @@ class Mamba(nn.Module):
     # ---- recurrent decode (no reference counterpart) -------------------------
     def allocate_inference_cache(self, batch_size, max_seqlen=None, dtype=None):
         mixers = [l.mixer if self.layout == "P" else l for l in self.layers]
-        return [m.allocate_inference_cache(batch_size, max_seqlen, dtype) for m in mixers]
+        return InferenceCache(m.allocate_inference_cache(batch_size, max_seqlen, dtype) for m in mixers)
 
     @torch.no_grad()
     def prefill(self, tokens, meta, cache):
@@ -302,14 +321,22 @@ class Mamba(nn.Module):
     def step(self, token, cache):
         """token [B] long -> logits [B, V]; advances every layer's state by one position."""
         tok = self.embedding if self.layout == "P" else self.token_embedding
+        mixers = [l.mixer if self.layout == "P" else l for l in self.layers]
+        consts = getattr(cache, "consts", None)
+        if consts is None:
+            consts = [m.step_constants() for m in mixers]
+            try:
+                cache.consts = consts
+            except AttributeError:  # a plain list was passed: rebuilt per call
+                pass
         x = tok(token)
         if self.layout == "S":
-            for layer, (cs, hs) in zip(self.layers, cache):
-                x = layer.step(x, cs, hs)
+            for layer, (cs, hs), k in zip(self.layers, cache, consts):
+                x = layer.step(x, cs, hs, k)
             return self.output_layer(self.norm(x))
         resid, hidden = x, None
-        for layer, (cs, hs) in zip(self.layers, cache):
+        for layer, (cs, hs), k in zip(self.layers, cache, consts):
             normed, resid = layer.norm(hidden, resid)
-            hidden = layer.mixer.step(normed, cs, hs)
+            hidden = layer.mixer.step(normed, cs, hs, k)
         normed, _ = self.norm_f(hidden, resid)
         return self.lm_head(normed)
