@@ -14,7 +14,7 @@ EXPORTS = [
     "mamba_abi_version", "mamba_last_error", "mamba_launch_count",
     "mamba_scan_fwd", "mamba_scan_ckpt_elems", "mamba_scan_bwd", "mamba_scan_bwd_workspace_bytes",
     "mamba_conv1d_silu_fwd", "mamba_conv1d_silu_bwd", "mamba_conv1d_bwd_workspace_bytes",
-    "mamba_conv_step", "mamba_ssm_step",
+    "mamba_conv_step", "mamba_ssm_step", "mamba_linear_step",
     "mamba_rmsnorm_fwd", "mamba_rmsnorm_bwd", "mamba_rmsnorm_bwd_workspace_bytes",
     "mamba_filtered_ce_fwd", "mamba_filtered_ce_bwd", "mamba_filtered_ce_workspace_bytes",
 ]
@@ -67,6 +67,11 @@ class NormArgs(C.Structure):
                 ("workspace_bytes", sz)]
 
 
+class LinearStepArgs(C.Structure):
+    _fields_ = [("struct_size", i32), ("dtype", i32), ("w_dtype", i32), ("batch", i32), ("in_features", i32),
+                ("out_features", i32), ("x", vp), ("x_bs", i64), ("weight", vp), ("bias", vp), ("y", vp), ("y_bs", i64)]
+
+
 class LossArgs(C.Structure):
     _fields_ = [("struct_size", i32), ("dtype", i32), ("batch", i32), ("seqlen", i32), ("vocab", i32),
                 ("boundaries", i32 * 4), ("reserved", i32),
@@ -99,7 +104,8 @@ def lib() -> C.CDLL:
                        ("mamba_conv1d_silu_fwd", ConvArgs), ("mamba_conv1d_silu_bwd", ConvArgs),
                        ("mamba_conv_step", StepArgs), ("mamba_ssm_step", StepArgs),
                        ("mamba_rmsnorm_fwd", NormArgs), ("mamba_rmsnorm_bwd", NormArgs),
-                       ("mamba_filtered_ce_fwd", LossArgs), ("mamba_filtered_ce_bwd", LossArgs)):
+                       ("mamba_filtered_ce_fwd", LossArgs), ("mamba_filtered_ce_bwd", LossArgs),
+                       ("mamba_linear_step", LinearStepArgs)):
         f = getattr(L, name)
         f.restype = C.c_int
         f.argtypes = [C.POINTER(argt), C.c_void_p]

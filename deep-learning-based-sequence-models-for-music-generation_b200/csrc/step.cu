@@ -80,6 +80,61 @@ __global__ void __launch_bounds__(256) ssm_step_kernel(const StepParams p) {
   }
 }
 
+// Bandwidth-shaped variant (N % 4 == 0, R % 4 == 0, 16-byte aligned rows): a HALF-warp owns one (b, d) pair, so a
+// warp instruction touches two full 256-byte state rows with 128-bit accesses; the fused dt_proj row-dot and the
+// <h, C> reduction are 4 butterfly steps inside the half-warp.  All (b, d) pairs are independent, so the grid
+// covers them all at once instead of looping over the batch.
+template <typename T>
+__global__ void __launch_bounds__(256) ssm_step_fast_kernel(const StepParams p) {
+  const int hl = threadIdx.x & 15;
+  const int64_t item = (int64_t)blockIdx.x * (blockDim.x >> 4) + (threadIdx.x >> 4);
+  if (item >= (int64_t)p.B * p.D) return;  // whole half-warps leave together; shuffles below use per-half masks
+  const unsigned mask = 0xffffu << (threadIdx.x & 16);
+  const int b = (int)(item / p.D), d = (int)(item - (int64_t)b * p.D);
+  float dot = 0.f;
+  {
+    const float* w = p.dtw + (int64_t)d * p.R;
+    const T* x = static_cast<const T*>(p.dt_in) + (int64_t)b * p.dt_in_bs;
+    for (int r4 = hl; r4 < (p.R >> 2); r4 += 16) {
+      const float4 wv = __ldg(reinterpret_cast<const float4*>(w) + r4);
+      float xv[4];
+      V4<T>::ld(x + 4 * r4, xv);
+      dot = fmaf(wv.x, xv[0], fmaf(wv.y, xv[1], fmaf(wv.z, xv[2], fmaf(wv.w, xv[3], dot))));
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) dot += __shfl_xor_sync(mask, dot, o);
+  }
+  dot += p.dtb ? p.dtb[d] : 0.f;
+  const float delta = (p.flags & MAMBA_FLAG_DELTA_SOFTPLUS) ? softplus_fast(dot) : dot;
+  const float xc = IO<T>::ld(static_cast<const T*>(p.xc) + (int64_t)b * p.xc_bs + d);
+  const float du = delta * xc, dl2 = delta * kLog2e;
+  float* h = p.h + ((int64_t)b * p.D + d) * p.N;
+  const float* A = p.A + (int64_t)d * p.N;
+  const T* Bv = static_cast<const T*>(p.Bv) + (int64_t)b * p.Bv_bs;
+  const T* Cv = static_cast<const T*>(p.Cv) + (int64_t)b * p.Cv_bs;
+  float y = 0.f;
+  for (int n4 = hl; n4 < (p.N >> 2); n4 += 16) {
+    const float4 a4 = __ldg(reinterpret_cast<const float4*>(A) + n4);
+    float4 h4 = reinterpret_cast<float4*>(h)[n4];
+    float bb[4], cc[4];
+    V4<T>::ld(Bv + 4 * n4, bb);
+    V4<T>::ld(Cv + 4 * n4, cc);
+    h4.x = fmaf(ex2_approx(dl2 * a4.x), h4.x, du * bb[0]);
+    h4.y = fmaf(ex2_approx(dl2 * a4.y), h4.y, du * bb[1]);
+    h4.z = fmaf(ex2_approx(dl2 * a4.z), h4.z, du * bb[2]);
+    h4.w = fmaf(ex2_approx(dl2 * a4.w), h4.w, du * bb[3]);
+    reinterpret_cast<float4*>(h)[n4] = h4;
+    y = fmaf(h4.x, cc[0], fmaf(h4.y, cc[1], fmaf(h4.z, cc[2], fmaf(h4.w, cc[3], y))));
+  }
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) y += __shfl_xor_sync(mask, y, o);
+  if (hl == 0) {
+    y = fmaf((p.flags & MAMBA_FLAG_HAS_D) ? p.Dv[d] : 0.f, xc, y);
+    if (p.flags & MAMBA_FLAG_HAS_Z) y *= silu_fast(IO<T>::ld(static_cast<const T*>(p.z) + (int64_t)b * p.z_bs + d));
+    IO<T>::st(static_cast<T*>(p.y) + (int64_t)b * p.y_bs + d, y);
+  }
+}
+
 static int step_common(const MambaStepArgs* a, StepParams& p, const char* what) {
   if (!a || a->struct_size != (int32_t)sizeof(MambaStepArgs))
     return set_error(MAMBA_EINVAL, "%s: bad args pointer or struct_size", what);
@@ -126,12 +181,27 @@ extern "C" int mamba_ssm_step(const MambaStepArgs* a, void* stream) {
   if ((a->flags & MAMBA_FLAG_HAS_Z) && !a->z) return set_error(MAMBA_EINVAL, "ssm_step: HAS_Z but z == NULL");
   if ((a->flags & MAMBA_FLAG_HAS_D) && !a->D) return set_error(MAMBA_EINVAL, "ssm_step: HAS_D but D == NULL");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int warps = 8;
-  const int blocks = ceil_div(p.D, warps);
-  if (a->dtype == MAMBA_F32)
-    ssm_step_kernel<float><<<blocks, warps * 32, 0, st>>>(p);
-  else
-    ssm_step_kernel<__nv_bfloat16><<<blocks, warps * 32, 0, st>>>(p);
+  const size_t elt = a->dtype == MAMBA_F32 ? 4 : 2;
+  auto al = [&](const void* q, int64_t stride, size_t e) {
+    return reinterpret_cast<uintptr_t>(q) % (4 * e) == 0 && (stride * e) % (4 * e) == 0;
+  };
+  const bool fast = p.N % 4 == 0 && p.R % 4 == 0 && aligned16(a->dt_weight) && aligned16(a->A) && aligned16(a->ssm_state) &&
+                    al(a->dt_in, a->dt_in_bs, elt) && al(a->Bv, a->Bv_bs, elt) && al(a->Cv, a->Cv_bs, elt);
+  if (fast) {
+    const int64_t items = (int64_t)p.B * p.D;
+    const int blocks = (int)((items + 15) / 16);
+    if (a->dtype == MAMBA_F32)
+      ssm_step_fast_kernel<float><<<blocks, 256, 0, st>>>(p);
+    else
+      ssm_step_fast_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(p);
+  } else {
+    const int warps = 8;
+    const int blocks = ceil_div(p.D, warps);
+    if (a->dtype == MAMBA_F32)
+      ssm_step_kernel<float><<<blocks, warps * 32, 0, st>>>(p);
+    else
+      ssm_step_kernel<__nv_bfloat16><<<blocks, warps * 32, 0, st>>>(p);
+  }
   count_launch();
   return check_launch("ssm_step");
 }

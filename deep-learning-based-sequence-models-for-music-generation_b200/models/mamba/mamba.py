@@ -69,6 +69,14 @@ def _act_dtype(x: torch.Tensor) -> torch.dtype:
     return x.dtype
 
 
+def _linear_step(x, lin):
+    """nn.Linear for one position per sequence: the weight-streaming kernel for <= 16 rows, cuBLAS otherwise."""
+    if x.shape[0] <= 16 and x.shape[1] % 4 == 0 and lin.weight.is_contiguous():
+        return ops.linear_step(x.contiguous() if x.stride(-1) != 1 else x, lin.weight.detach(),
+                               None if lin.bias is None else lin.bias.detach())
+    return lin(x)
+
+
 class RMSNorm(nn.Module):  # simple_mamba @L336-348
     def __init__(self, d_model: int, eps: float = 1e-5):
         super().__init__()
@@ -159,17 +167,15 @@ class MambaBlock(nn.Module):  # simple_mamba @L184
         p = self.params
         k = consts if consts is not None else self.step_constants()
         T = conv_state.dtype                                              # the step's activation dtype
-        xz = self.in_proj(x_t)                                            # [B, 2*d_inner]
-        if xz.dtype != T:
-            xz = xz.to(T)
+        if x_t.dtype != T:
+            x_t = x_t.to(T)
+        xz = _linear_step(x_t, self.in_proj)                              # [B, 2*d_inner]
         xs, res = xz.split([p.d_inner, p.d_inner], dim=-1)
         xc = ops.conv_step(xs, conv_state, k["conv_w"], k["conv_b"])
-        x_dbl = self.x_proj(xc)
-        if x_dbl.dtype != T:
-            x_dbl = x_dbl.to(T)
+        x_dbl = _linear_step(xc, self.x_proj)
         dt_r, Bv, Cv = x_dbl.split([p.dt_rank, p.d_state, p.d_state], dim=-1)
         y = ops.ssm_step(xc, dt_r, Bv, Cv, k["dt_w"], k["dt_b"], k["A"], k["D"], res, ssm_state)
-        return self.out_proj(y)
+        return _linear_step(y, self.out_proj)
 
 
 class ResidualBlock(nn.Module):  # simple_mamba @L151-181
@@ -333,10 +339,10 @@ class Mamba(nn.Module):
         if self.layout == "S":
             for layer, (cs, hs), k in zip(self.layers, cache, consts):
                 x = layer.step(x, cs, hs, k)
-            return self.output_layer(self.norm(x))
+            return _linear_step(self.norm(x), self.output_layer)
         resid, hidden = x, None
         for layer, (cs, hs), k in zip(self.layers, cache, consts):
             normed, resid = layer.norm(hidden, resid)
             hidden = layer.mixer.step(normed, cs, hs, k)
         normed, _ = self.norm_f(hidden, resid)
-        return self.lm_head(normed)
+        return _linear_step(normed, self.lm_head)

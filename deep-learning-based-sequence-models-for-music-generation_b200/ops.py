@@ -19,7 +19,7 @@ import torch
 
 from . import _lib
 from ._lib import (FLAG_DELTA_SOFTPLUS, FLAG_HAS_D, FLAG_HAS_DELTA_BIAS, FLAG_HAS_Z, MAMBA_BF16, MAMBA_F32, ConvArgs,
-                   LossArgs, NormArgs, ScanBwdArgs, ScanFwdArgs, StepArgs, check, lib)
+                   LinearStepArgs, LossArgs, NormArgs, ScanBwdArgs, ScanFwdArgs, StepArgs, check, lib)
 
 _DTYPES = {torch.float32: MAMBA_F32, torch.bfloat16: MAMBA_BF16}
 
@@ -498,6 +498,30 @@ def ssm_step(xc, dt_in, Bv, Cv, dt_weight, dt_bias, A, D, z, ssm_state, delta_so
     a.ssm_state = _p(ssm_state)
     a.y, a.y_bs = _p(y), y.stride(0)
     _call("mamba_ssm_step", a, xc.device)
+    return y
+
+
+@torch.no_grad()
+def linear_step(x, weight, bias=None):
+    """y = x @ weight.T (+ bias) for x [B <= 16, K]: the weight-streaming decode form of nn.Linear."""
+    _require_cuda(x, weight, bias)
+    if x.dim() != 2 or x.stride(-1) != 1:
+        raise ValueError("linear_step: x must be [B, K] with unit inner stride")
+    Bsz, K = x.shape
+    N = weight.shape[0]
+    if weight.shape[1] != K or not weight.is_contiguous():
+        raise ValueError("linear_step: weight must be contiguous [N, K]")
+    if bias is not None and bias.dtype != weight.dtype:
+        bias = bias.to(weight.dtype)
+    y = torch.empty((Bsz, N), dtype=x.dtype, device=x.device)
+    a = LinearStepArgs()
+    a.struct_size = ct.sizeof(LinearStepArgs)
+    a.dtype, a.w_dtype = _dtype_code(x), _dtype_code(weight)
+    a.batch, a.in_features, a.out_features = Bsz, K, N
+    a.x, a.x_bs = _p(x), x.stride(0)
+    a.weight, a.bias = _p(weight), _p(bias)
+    a.y, a.y_bs = _p(y), y.stride(0)
+    _call("mamba_linear_step", a, x.device)
     return y
 
 

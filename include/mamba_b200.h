@@ -208,6 +208,24 @@ int mamba_conv_step(const MambaStepArgs* args, void* stream);
 int mamba_ssm_step(const MambaStepArgs* args, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * One-position linear layer (decode).  Replaces the nn.Linear calls of the block for ONE new position per
+ * sequence: in_proj (simple_mamba.pyc @L230), x_proj (@L273), out_proj (@L243), lm_head (@L94):
+ *     y[b, :] = weight @ x[b, :] (+ bias),   weight [out_features, in_features] row-major (nn.Linear.weight)
+ * batch <= 16, in_features % 4 == 0.  `dtype` is the element type of x and y, `w_dtype` of weight and bias.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct MambaLinearStepArgs {
+  int32_t struct_size;
+  int32_t dtype, w_dtype;
+  int32_t batch, in_features, out_features;
+  const void* x;      int64_t x_bs;   /* [B, in_features]  */
+  const void* weight;                 /* [out_features, in_features] contiguous */
+  const void* bias;                   /* [out_features] or NULL */
+  void* y;            int64_t y_bs;   /* [B, out_features] */
+} MambaLinearStepArgs;
+
+int mamba_linear_step(const MambaLinearStepArgs* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * RMSNorm with fused residual add.  Replaces RMSNorm.forward (simple_mamba.pyc @L346) and the
  * `+ x` of ResidualBlock.forward (@L179):
  *     r = x + residual   (either operand may be NULL, not both; the sum is rounded to resid_dtype

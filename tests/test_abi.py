@@ -38,7 +38,7 @@ def test_ctypes_struct_layout_matches_c(tmp_path):
     from mamba_b200 import _lib
     structs = {"MambaScanFwdArgs": _lib.ScanFwdArgs, "MambaScanBwdArgs": _lib.ScanBwdArgs,
                "MambaConvArgs": _lib.ConvArgs, "MambaStepArgs": _lib.StepArgs, "MambaNormArgs": _lib.NormArgs,
-               "MambaLossArgs": _lib.LossArgs}
+               "MambaLossArgs": _lib.LossArgs, "MambaLinearStepArgs": _lib.LinearStepArgs}
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void){"]
     for cname, ct in structs.items():
         lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')

@@ -402,3 +402,27 @@ def test_scan_kernel_matches_reference_golden_vector():
     g = {k: v.cuda() for k, v in f.items()}
     y = ops.selective_scan_fn(g["u"], g["delta"], g["A"], g["B"], g["C"], g["D"])
     assert_close(y, f["y"], RTOL32, what="CUDA scan vs reference golden")
+
+
+@pytest.mark.parametrize("cfg", [(1, 64, 32), (10, 1024, 4096), (10, 2048, 192), (16, 128, 17914), (3, 36, 40)])
+@pytest.mark.parametrize("dtypes", [(torch.float32, torch.float32), (torch.bfloat16, torch.bfloat16),
+                                    (torch.float32, torch.bfloat16)])
+def test_linear_step_matches_matmul(cfg, dtypes):
+    """mamba_linear_step (decode GEMV) against the fp64 product of the same rounded operands."""
+    from mamba_b200 import ops
+    B, K, N = cfg
+    tx, tw = dtypes
+    g = torch.Generator().manual_seed(K + N)
+    x = torch.randn(B, K, generator=g).to(tx)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(tw)
+    bias = torch.randn(N, generator=g).to(tw)
+    ref = x.double() @ w.double().T + bias.double()
+    y = ops.linear_step(x.cuda(), w.cuda(), bias.cuda())
+    assert y.dtype == tx and y.shape == (B, N)
+    if tx == torch.float32:
+        assert_close(y, ref, 1e-4, 1e-5, what=f"linear_step {cfg} {dtypes}")
+    else:
+        assert_close(y, ref, RTOL16, FLOOR16, what=f"linear_step {cfg} {dtypes}")
+    y2 = ops.linear_step(x.cuda(), w.cuda(), None)
+    assert_close(y2.float().cpu() + bias.float(), ref, 1e-4 if tx == torch.float32 else RTOL16,
+                 1e-5 if tx == torch.float32 else FLOOR16, what="linear_step no bias")
