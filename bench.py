@@ -177,6 +177,20 @@ def algorithmic_bytes(B, L, D, N, K, s):
     }
 
 
+MUFU_EX2_PEAK = 4.6e12  # ex2/s, measured on this pool's B200 with tools/microbench.cu (16 lanes/clk/SM at 1.965 GHz)
+
+
+def mufu_view(name, B, L, D, N, mean_us):
+    """The scan kernels execute one (forward) or two (backward) MUFU.EX2 per (b, t, d, n): at d_state 64 that pipe,
+    not HBM, is what binds them.  Reported next to the mandatory HBM roofline."""
+    per = {"mamba_scan_fwd": 1, "mamba_scan_bwd": 2}.get(name)
+    if per is None:
+        return None
+    rate = per * B * L * D * N / (mean_us * 1e-6)
+    return {"pipe": "mufu_ex2", "achieved": rate, "peak": MUFU_EX2_PEAK, "unit": "ex2/s", "frac": rate / MUFU_EX2_PEAK,
+            "peak_source": "measured (tools/microbench.cu, gpurun_out/microbench.txt)"}
+
+
 def kernel_times(trainer, batches, reps=3):
     import torch
     from mamba_b200 import ops
@@ -201,6 +215,72 @@ def kernel_times(trainer, batches, reps=3):
     return out
 
 
+def extras(dev, peak):
+    """(a) kernel-only selective-scan sweep at BASELINE configs[4] (L=8192, N=16, D=2048) and at the repo's training
+    shape, fp32, CUDA events, L2 flushed between launches; (b) recurrent greedy decode, 10 sequences (5 composer
+    conditions x 2), 2048-token prompt."""
+    import torch
+    from mamba_b200 import generate, ops, synthetic, train
+    out = {"scan_sweep": [], "peak_gbs": peak}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for name, (B, L, D, N) in (("config5_B2_L8192_N16", (2, 8192, 2048, 16)), ("config5_B8_L8192_N16", (8, 8192, 2048, 16)),
+                               ("repo_B2_L2054_N64", (2, 2054, 2048, 64))):
+        g = torch.Generator(device=dev).manual_seed(0)
+        u, z = (torch.randn(B, L, D, device=dev, generator=g) for _ in range(2))
+        dl = torch.randn(B, L, D, device=dev, generator=g) - 4
+        A = -torch.arange(1, N + 1, device=dev, dtype=torch.float32).repeat(D, 1)
+        Bm, Cm = (torch.randn(B, L, N, device=dev, generator=g) for _ in range(2))
+        Dv, bias = torch.ones(D, device=dev), torch.zeros(D, device=dev)
+        dout = torch.randn(B, L, D, device=dev, generator=g)
+        leaves = [t.requires_grad_(True) for t in (u, dl, A, Bm, Cm, Dv, z, bias)]
+
+        def timeit(fn, iters=5):
+            fn()
+            ts = []
+            for _ in range(iters):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fn()
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1) * 1e3)
+            return sorted(ts)[len(ts) // 2]
+
+        with torch.no_grad():
+            t_f = timeit(lambda: ops.selective_scan_fn(u, dl, A, Bm, Cm, Dv, z=z, delta_bias=bias, delta_softplus=True))
+        o = ops.selective_scan_fn(*leaves[:6], z=leaves[6], delta_bias=leaves[7], delta_softplus=True)
+        t_b = timeit(lambda: torch.autograd.grad(o, leaves, dout, retain_graph=True))
+        by = algorithmic_bytes(B, L, D, N, 4, 4)
+        out["scan_sweep"].append({"shape": name, "dtype": "f32", "fwd_us": t_f, "bwd_us": t_b,
+                                  "fwd_gbs": by["mamba_scan_fwd"] / t_f / 1e3, "bwd_gbs": by["mamba_scan_bwd"] / t_b / 1e3,
+                                  "fwd_frac_hbm": by["mamba_scan_fwd"] / t_f / 1e3 / peak,
+                                  "bwd_frac_hbm": by["mamba_scan_bwd"] / t_b / 1e3 / peak,
+                                  "elem_per_s": B * L * D * N / (t_f * 1e-6)})
+        del leaves, o, u, z, dl, Bm, Cm, dout
+    del flush
+    torch.manual_seed(0)
+    model = train.new_model("mamba").to(dev).eval()
+    src, _, meta = synthetic.batch(10, 2048, seed=3)
+    with torch.no_grad():
+        dec = generate.RecurrentDecoder(model, 10, use_graph=True)
+        dec.prefill(src.to(dev), meta.to(dev))
+        for _ in range(8):
+            dec.step()
+        torch.cuda.synchronize()
+        n = 200
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            dec.step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+    out["decode"] = {"sequences": 10, "prompt": 2048, "timed_tokens_per_seq": n, "dtype": "f32", "ms_per_step": ms / n,
+                     "tokens_per_sec": 10 * n / (ms * 1e-3), "mode": "recurrent step kernels, one CUDA graph per token, greedy"}
+    return out
+
+
 # ----------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -210,6 +290,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
     args = ap.parse_args()
     if args.impl == "reference":
@@ -344,9 +425,17 @@ def main():
         line["roofline"] = {"kernel": dom, "bound": "hbm", "achieved": d["achieved_gbs"], "peak": peak, "unit": "GB/s",
                             "frac": d["frac_of_hbm_peak"], "traffic": None, "peak_source": peak_src,
                             "mean_us": d["mean_us"], "algorithmic_bytes": d["algorithmic_bytes"],
+                            "binding_pipe": mufu_view(dom, B, T + cc.N_META, p.d_inner, p.d_state, d["mean_us"]),
                             "note": "d_state=64 makes this kernel MUFU/FMA-bound, not HBM-bound (SURVEY.md F8); "
                                     "see profiles/ for the ncu pipe utilisation"}
         line["kernels"] = per_kernel
+        # ---- the other two figures of BASELINE.json's metric, N=1 only (short runs; tools/bench_scan.py and
+        #      tools/bench_decode.py are the full versions) ---------------------------------------------------------
+        if world == 1 and not args.no_extras:
+            try:
+                line["extras"] = extras(dev, peak)
+            except Exception as e:  # never lose the headline line to an extra
+                line["extras"] = {"error": str(e)[:200]}
         # ---- CPU baseline (oracle port) on this box's host cores, N=1 only ----------------------------------
         if world == 1 and not args.no_cpu_baseline:
             tps, ms, cores, sample = cpu_reference_sample(steps=2, warmup=1)
