@@ -15,7 +15,7 @@
 //     before step t is computed.
 //   * HELPER warps (4) run everything else through shared-memory rings: cp.async (LDGSTS, 16 B) loads RR stages
 //     ahead (enough bytes in flight to cover HBM latency with one CTA per SM), the pre-pass (softplus(delta +
-//     bias), delta*u; bf16 -> fp32 B/C), and the post-pass (sum of the per-warp partials, + D*u, * silu(z),
+//     bias), delta*u), and the post-pass (sum of the per-warp partials, + D*u, * silu(z),
 //     128-bit coalesced store).  Each helper thread owns (timestep, 4 consecutive channels) of a stage.
 //   * producer/consumer hand-off uses named barriers (bar.arrive / bar.sync), two per work slot.
 //   * every 16 timesteps the scan warps checkpoint h to HBM ([B, nck, N, D], coalesced) for the backward.
@@ -43,14 +43,21 @@ struct ScanFwdParams {
   int vec_u, vec_delta, vec_z, vec_B, vec_C, vec_out, vec_ypre;
 };
 
+// 4 consecutive shared-memory elements as a float4 (bf16 widened in registers)
+__device__ __forceinline__ float4 ld4_as_f32(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 ld4_as_f32(const __nv_bfloat16* p) {
+  const uint2 v = *reinterpret_cast<const uint2*>(p);
+  return make_float4(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xffff0000u), __uint_as_float(v.y << 16),
+                     __uint_as_float(v.y & 0xffff0000u));
+}
+
 // Shared-memory layout.  RAW ring slot (cp.async targets, element type T):
 //     u[TS][32], delta[TS][32], z[TS][32], B[TS][NPT], C[TS][NPT]
-// WORK slot (two of them):  dlu[TS][32] float2 = (softplus(delta+bias), that * u),  ypart[NS][TS][32] fp32,
-//     and for bf16 I/O the fp32 copies Bf[TS][NPT], Cf[TS][NPT].
+// WORK slot (two of them):  dlu[TS][32] float2 = (softplus(delta+bias), that * u),  ypart[NS][TS][32] fp32.
 template <typename T>
 struct FwdLayout {
   int raw_u, raw_dl, raw_z, raw_B, raw_C, raw_bytes;
-  int w_dlu, w_y, w_Bf, w_Cf, work_bytes;
+  int w_dlu, w_y, work_bytes;
   __host__ __device__ FwdLayout(int NS, int NPT) {
     int o = 0;
     raw_u = o, o += kTS * kDT * (int)sizeof(T);
@@ -62,8 +69,6 @@ struct FwdLayout {
     o = 0;
     w_dlu = o, o += kTS * kDT * 8;
     w_y = o, o += NS * kTS * kDT * 4;
-    w_Bf = o, o += (sizeof(T) == 4 ? 0 : kTS * NPT * 4);
-    w_Cf = o, o += (sizeof(T) == 4 ? 0 : kTS * NPT * 4);
     work_bytes = (o + 127) & ~127;
   }
 };
@@ -103,10 +108,11 @@ __global__ void __launch_bounds__((kMaxScanWarps + kHelperWarps) * 32) scan_fwd_
       unsigned char* wbase = work_base + (size_t)ws * lay.work_bytes;
       unsigned char* rbase = raw_base + (size_t)rslot * lay.raw_bytes;
       const float2* dlu = reinterpret_cast<const float2*>(wbase + lay.w_dlu) + lane;
-      const float* Bf = (sizeof(T) == 4 ? reinterpret_cast<const float*>(rbase + lay.raw_B)
-                                        : reinterpret_cast<const float*>(wbase + lay.w_Bf)) + s * NPER;
-      const float* Cf = (sizeof(T) == 4 ? reinterpret_cast<const float*>(rbase + lay.raw_C)
-                                        : reinterpret_cast<const float*>(wbase + lay.w_Cf)) + s * NPER;
+      // B / C are read from the raw (cp.async) tiles in their storage dtype; bf16 is widened in registers (two
+      // ALU ops per pair on the otherwise idle integer pipe) so that no helper round trip sits between the load
+      // landing and the scan using it
+      const T* Bf = reinterpret_cast<const T*>(rbase + lay.raw_B) + s * NPER;
+      const T* Cf = reinterpret_cast<const T*>(rbase + lay.raw_C) + s * NPER;
       float* yp = reinterpret_cast<float*>(wbase + lay.w_y) + (s * kTS) * kDT + lane;
       bar_sync(1 + ws, bar_count);  // stage c prepared
       // Operands of timestep t+1 are fetched BEFORE timestep t is computed and stored: ptxas will not move a
@@ -117,8 +123,8 @@ __global__ void __launch_bounds__((kMaxScanWarps + kHelperWarps) * 32) scan_fwd_
         dd = dlu[t * kDT];
 #pragma unroll
         for (int q = 0; q < NPER / 4; ++q) {
-          Bv[q] = *reinterpret_cast<const float4*>(Bf + t * NPT + 4 * q);
-          Cv[q] = *reinterpret_cast<const float4*>(Cf + t * NPT + 4 * q);
+          Bv[q] = ld4_as_f32(Bf + t * NPT + 4 * q);
+          Cv[q] = ld4_as_f32(Cf + t * NPT + 4 * q);
         }
       };
       fetch(0, dd_cur, Bc, Cc);
@@ -285,16 +291,6 @@ __global__ void __launch_bounds__((kMaxScanWarps + kHelperWarps) * 32) scan_fwd_
     float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float2*>(wbase + lay.w_dlu) + my_t * kDT + my_c);
     dst[0] = make_float4(r[0], r[1], r[2], r[3]);
     dst[1] = make_float4(r[4], r[5], r[6], r[7]);
-    if (sizeof(T) != 4) {
-      const T* sB = reinterpret_cast<const T*>(rbase + lay.raw_B);
-      const T* sC = reinterpret_cast<const T*>(rbase + lay.raw_C);
-      float* Bf = reinterpret_cast<float*>(wbase + lay.w_Bf);
-      float* Cf = reinterpret_cast<float*>(wbase + lay.w_Cf);
-      for (int i = ht; i < kTS * NPT; i += kHelperThreads) {
-        Bf[i] = IO<T>::cvt(sB[i]);
-        Cf[i] = IO<T>::cvt(sC[i]);
-      }
-    }
   };
 
   auto post_pass = [&](int c, int rslot) {
