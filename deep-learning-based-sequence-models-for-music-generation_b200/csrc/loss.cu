@@ -170,20 +170,51 @@ __global__ void loss_colsum_combine_kernel(const LossParams p) {
   p.colsum[(int64_t)b * p.V + v] = acc;
 }
 
-// (4) grid (ceil(V / (threads)), B*T)
-template <typename T>
+// (4) grid (ceil(V / (threads * VEC)), B*T): VEC consecutive vocab entries per thread (128-bit / 64-bit accesses when
+//     the logits rows are 4-element aligned, which the padded LM-head output is)
+template <typename T, int VEC>
 __global__ void __launch_bounds__(256) loss_dlogits_kernel(const LossParams p) {
   const int row = blockIdx.y;
   const int b = row / p.T, t = row - b * p.T;
-  const int v = blockIdx.x * blockDim.x + threadIdx.x;
-  if (v >= p.V) return;
-  const float x = IO<T>::ld(static_cast<const T*>(p.logits) + (int64_t)b * p.l_bs + (int64_t)t * p.l_ts + v);
-  const float cl = p.col_lse[(int64_t)b * p.V + v];
-  const float w = p.table[(int64_t)bucket_of(p.src[row], p.bnd) * p.V + v];
+  const int v0 = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+  if (v0 >= p.V) return;
+  const T* xr = static_cast<const T*>(p.logits) + (int64_t)b * p.l_bs + (int64_t)t * p.l_ts + v0;
+  T* gr = static_cast<T*>(p.dlogits) + (int64_t)b * p.d_bs + (int64_t)t * p.d_ts + v0;
+  const float* cl = p.col_lse + (int64_t)b * p.V + v0;
+  const float* cs = p.colsum + (int64_t)b * p.V + v0;
+  const float* w = p.table + (int64_t)bucket_of(p.src[row], p.bnd) * p.V + v0;
   const float scale = (p.grad_out ? p.grad_out[0] : 1.f) / (float)(p.B * p.T);
-  const float dlp = dlp_of<T>(p, x, cl, w, p.row_lse[row], p.trg[row] == v, scale);
-  const float g = dlp - exp_fast(x - cl) * p.colsum[(int64_t)b * p.V + v];
-  IO<T>::st(static_cast<T*>(p.dlogits) + (int64_t)b * p.d_bs + (int64_t)t * p.d_ts + v, g);
+  const float rl = p.row_lse[row];
+  const int tg = (int)p.trg[row] - v0;
+  float x[VEC], g[VEC];
+  if (VEC == 4 && v0 + 4 <= p.V) {
+    float xv[4];
+    V4<T>::ld(xr, xv);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) x[e] = xv[e];
+  } else {
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) x[e] = v0 + e < p.V ? IO<T>::ld(xr + e) : 0.f;
+  }
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) {
+    if (v0 + e < p.V) {
+      const float dlp = dlp_of<T>(p, x[e], cl[e], w[e], rl, tg == e, scale);
+      g[e] = dlp - exp_fast(x[e] - cl[e]) * cs[e];
+    } else {
+      g[e] = 0.f;
+    }
+  }
+  if (VEC == 4 && v0 + 4 <= p.V) {
+    float gv[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) gv[e] = g[e < VEC ? e : 0];
+    V4<T>::st_global(gr, gv);
+  } else {
+#pragma unroll
+    for (int e = 0; e < VEC; ++e)
+      if (v0 + e < p.V) IO<T>::st(gr + e, g[e]);
+  }
 }
 
 static int loss_fill(const MambaLossArgs* a, LossParams& p, bool bwd) {
@@ -231,7 +262,13 @@ static int loss_bwd_launch(const LossParams& p, cudaStream_t st) {
   dim3 gcol(ceil_div(p.V, kLossColThreads), p.S, p.B);
   loss_colsum_kernel<T><<<gcol, kLossColThreads, 0, st>>>(p);
   loss_colsum_combine_kernel<<<dim3(ceil_div(p.V, 256), p.B), 256, 0, st>>>(p);
-  loss_dlogits_kernel<T><<<dim3(ceil_div(p.V, 256), p.B * p.T), 256, 0, st>>>(p);
+  const size_t elt = sizeof(T);
+  const bool vec = reinterpret_cast<uintptr_t>(p.logits) % (4 * elt) == 0 && reinterpret_cast<uintptr_t>(p.dlogits) % (4 * elt) == 0 &&
+                   p.l_bs % 4 == 0 && p.l_ts % 4 == 0 && p.d_bs % 4 == 0 && p.d_ts % 4 == 0;
+  if (vec)
+    loss_dlogits_kernel<T, 4><<<dim3(ceil_div(p.V, 256 * 4), p.B * p.T), 256, 0, st>>>(p);
+  else
+    loss_dlogits_kernel<T, 1><<<dim3(ceil_div(p.V, 256), p.B * p.T), 256, 0, st>>>(p);
   count_launch(3);
   return check_launch("filtered_ce_bwd");
 }

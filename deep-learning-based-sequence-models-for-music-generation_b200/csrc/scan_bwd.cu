@@ -564,11 +564,21 @@ __global__ void scan_bwd_finalize_kernel(const ScanBwdParams p, int rows_per_blo
       const float* sB = p.ws_dB + (((int64_t)b * p.ntiles) * p.L + t) * p.N + n;
       const float* sC = p.ws_dC + (((int64_t)b * p.ntiles) * p.L + t) * p.N + n;
       const int64_t ts = (int64_t)p.L * p.N;
-      float accB = 0.f, accC = 0.f;
-      for (int k = 0; k < p.ntiles; ++k) {
-        accB += sB[k * ts];
-        accC += sC[k * ts];
+      // fixed-order sum with 8 loads in flight (4 interleaved partial sums, combined in a fixed order)
+      float aB[4] = {0.f, 0.f, 0.f, 0.f}, aC[4] = {0.f, 0.f, 0.f, 0.f};
+      int k = 0;
+      for (; k + 4 <= p.ntiles; k += 4) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          aB[q] += sB[(k + q) * ts];
+          aC[q] += sC[(k + q) * ts];
+        }
       }
+      for (; k < p.ntiles; ++k) {
+        aB[0] += sB[k * ts];
+        aC[0] += sC[k * ts];
+      }
+      const float accB = (aB[0] + aB[1]) + (aB[2] + aB[3]), accC = (aC[0] + aC[1]) + (aC[2] + aC[3]);
       IO<T>::st(static_cast<T*>(p.dB) + (int64_t)b * p.dB_bs + t * p.dB_ls + n, accB);
       IO<T>::st(static_cast<T*>(p.dC) + (int64_t)b * p.dC_bs + t * p.dC_ls + n, accC);
     }

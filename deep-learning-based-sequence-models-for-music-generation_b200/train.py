@@ -247,10 +247,13 @@ class Trainer:
         self.graph = None
 
     def _flatten_grads(self, bucket_mb):
-        self.grads = FlatGrads(self.model.parameters(), bucket_mb)
-        self.flat_grad = self.grads.flat
+        # one rank: autograd writes each gradient straight into a fresh buffer (no accumulate-add per parameter);
+        # several ranks: gradients live in one flat buffer so that the exchange is a few large all-reduces
+        self.grads = FlatGrads(self.model.parameters(), bucket_mb) if self.world_size > 1 else None
 
     def _allreduce(self):
+        if self.grads is None:
+            return
         if self.overlap:
             self.grads.finish()          # the buckets were launched from the backward hooks
         else:
@@ -260,7 +263,10 @@ class Trainer:
         with torch.autocast("cuda", dtype=self.autocast_dtype, enabled=self.autocast_dtype is not None):
             output = self.model(self.src, self.meta)
         loss = loss_fn(self.src, self.trg, output)
-        self.grads.zero()
+        if self.grads is None:
+            self.optimizer.zero_grad(set_to_none=True)
+        else:
+            self.grads.zero()
         loss.backward()
         self._allreduce()
         self.optimizer.step()
