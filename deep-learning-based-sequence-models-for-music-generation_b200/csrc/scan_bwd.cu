@@ -165,24 +165,29 @@ __global__ void __launch_bounds__((NW + kBHelperWarps) * 32, 1) scan_bwd_kernel(
       dhc[0][j] = dhc[1][j] = make_float2(0.f, 0.f);
     }
     // chunk-start state of chunk c from the forward's checkpoints (zero for chunk 0)
+    // checkpoint layout [B][nck][ceil(N/4)][D][4] (scan_fwd.cu): the NPER states of one channel are contiguous
+    const int N4 = (p.N + 3) >> 2;
     auto load_ckpt = [&](int c, float2 (&h)[2][NPER]) {
+      float v[4][NPER];
 #pragma unroll
-      for (int j = 0; j < NPER; ++j) {
-        const int n = nbase + j;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (c > 0 && n < p.N) {
-          const float* ck = p.ckpt + (((int64_t)b * nck + c) * p.N + n) * p.D + d0 + dl0;
-          if (p.vec_ck && dl0 + 4 <= dvalid) {
-            v = __ldg(reinterpret_cast<const float4*>(ck));
+      for (int i = 0; i < 4; ++i) {
+#pragma unroll
+        for (int j = 0; j < NPER; ++j) v[i][j] = 0.f;
+        if (c > 0 && dl0 + i < dvalid && nbase < p.N) {
+          const float* ck = p.ckpt + ((((int64_t)b * nck + c) * N4 + (nbase >> 2)) * p.D + d0 + dl0 + i) * 4 + (nbase & 3);
+          if constexpr (NPER == 4) {
+            const float4 t4 = __ldg(reinterpret_cast<const float4*>(ck));
+            v[i][0] = t4.x, v[i][1] = t4.y, v[i][2] = t4.z, v[i][3] = t4.w;
+          } else if constexpr (NPER == 2) {
+            const float2 t2 = __ldg(reinterpret_cast<const float2*>(ck));
+            v[i][0] = t2.x, v[i][1] = t2.y;
           } else {
-            if (dl0 + 0 < dvalid) v.x = ck[0];
-            if (dl0 + 1 < dvalid) v.y = ck[1];
-            if (dl0 + 2 < dvalid) v.z = ck[2];
-            if (dl0 + 3 < dvalid) v.w = ck[3];
+            v[i][0] = __ldg(ck);
           }
         }
-        h[0][j] = make_float2(v.x, v.y), h[1][j] = make_float2(v.z, v.w);
       }
+#pragma unroll
+      for (int j = 0; j < NPER; ++j) h[0][j] = make_float2(v[0][j], v[1][j]), h[1][j] = make_float2(v[2][j], v[3][j]);
     };
     float2 hnext[2][NPER];
     load_ckpt(nck - 1, hnext);
@@ -703,6 +708,7 @@ extern "C" int mamba_scan_bwd(const MambaScanBwdArgs* a, void* stream) {
     return set_error(MAMBA_EINVAL, "scan_bwd: null input or output pointer");
   if (a->chunk != 8 && a->chunk != 16) return set_error(MAMBA_EINVAL, "scan_bwd: chunk must be 8 or 16 (got %d)", a->chunk);
   if (a->seqlen > a->chunk && !a->ckpt) return set_error(MAMBA_EINVAL, "scan_bwd: ckpt == NULL");
+  if (a->ckpt && !aligned16(a->ckpt)) return set_error(MAMBA_EALIGN, "scan_bwd: ckpt must be 16-byte aligned");
   if ((a->flags & MAMBA_FLAG_HAS_Z) && (!a->z || !a->dz || !a->y_pre))
     return set_error(MAMBA_EINVAL, "scan_bwd: HAS_Z but z/dz/y_pre NULL");
   if ((a->flags & MAMBA_FLAG_HAS_D) && !a->D) return set_error(MAMBA_EINVAL, "scan_bwd: HAS_D but D == NULL");

@@ -32,7 +32,7 @@ constexpr int kMaxScanWarps = 16;
 constexpr int kMaxBCVec = 4;  // precomputed B/C cp.async slots per helper thread (fast path)
 
 struct ScanFwdParams {
-  int B, L, D, N, NS, NPT, nck, cki, flags;
+  int B, L, D, N, N4, NS, NPT, nck, cki, flags;
   const void *u, *delta, *Bm, *Cm, *z;
   void* out;
   int64_t u_bs, u_ls, delta_bs, delta_ls, B_bs, B_ls, C_bs, C_ls, z_bs, z_ls, out_bs, out_ls;
@@ -153,10 +153,12 @@ __global__ void __launch_bounds__((kMaxScanWarps + kHelperWarps) * 32) scan_fwd_
           // h is now the state at the start of checkpoint chunk (c*kTS + t + 1) / CKI
           const int tg_next = c * kTS + t + 1;
           if (p.ckpt != nullptr && tg_next < p.L && d < p.D) {
-            float* ck = p.ckpt + (((int64_t)b * p.nck + tg_next / CKI) * p.N + s * NPER) * p.D + d;
+            // layout [B][nck][ceil(N/4)][D][4]: one 16-byte store per 4 states, 512 contiguous bytes per warp
+            float4* ck = reinterpret_cast<float4*>(p.ckpt) +
+                         (((int64_t)b * p.nck + tg_next / CKI) * p.N4 + s * (NPER / 4)) * p.D + d;
 #pragma unroll
-            for (int j = 0; j < NPER; ++j)
-              if (s * NPER + j < p.N) ck[(int64_t)j * p.D] = (j & 1) ? h[j / 2].y : h[j / 2].x;
+            for (int q = 0; q < NPER / 4; ++q)
+              if (s * NPER + 4 * q < p.N) ck[(int64_t)q * p.D] = make_float4(h[2 * q].x, h[2 * q].y, h[2 * q + 1].x, h[2 * q + 1].y);
           }
         }
       }
@@ -415,7 +417,7 @@ static bool vec_ok(const void* ptr, int64_t bs, int64_t ls, size_t elt) {
 
 extern "C" size_t mamba_scan_ckpt_elems(int batch, int seqlen, int dim, int dstate, int chunk) {
   if (batch <= 0 || seqlen <= 0 || dim <= 0 || dstate <= 0 || chunk <= 0) return 0;
-  return (size_t)batch * mb::ceil_div(seqlen, chunk) * dstate * dim;
+  return (size_t)batch * mb::ceil_div(seqlen, chunk) * (4 * mb::ceil_div(dstate, 4)) * dim;
 }
 
 extern "C" int mamba_scan_fwd(const MambaScanFwdArgs* a, void* stream) {
@@ -433,11 +435,13 @@ extern "C" int mamba_scan_fwd(const MambaScanFwdArgs* a, void* stream) {
   if ((a->flags & MAMBA_FLAG_HAS_DELTA_BIAS) && !a->delta_bias)
     return set_error(MAMBA_EINVAL, "scan_fwd: HAS_DELTA_BIAS but delta_bias == NULL");
   if (a->dtype != MAMBA_F32 && a->dtype != MAMBA_BF16) return set_error(MAMBA_EDTYPE, "scan_fwd: dtype %d", a->dtype);
+  if (a->ckpt && !aligned16(a->ckpt)) return set_error(MAMBA_EALIGN, "scan_fwd: ckpt must be 16-byte aligned");
   if (a->ckpt && a->chunk != 8 && a->chunk != 16)
     return set_error(MAMBA_EINVAL, "scan_fwd: chunk must be 8 or 16 (got %d)", a->chunk);
 
   ScanFwdParams p{};
   p.B = a->batch, p.L = a->seqlen, p.D = a->dim, p.N = a->dstate, p.flags = a->flags;
+  p.N4 = (p.N + 3) / 4;
   p.cki = a->ckpt ? a->chunk : 16;
   p.nck = ceil_div(p.L, p.cki);
   p.u = a->u, p.delta = a->delta, p.Bm = a->B, p.Cm = a->C, p.z = a->z, p.out = a->out;

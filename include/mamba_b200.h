@@ -61,8 +61,8 @@ enum {
  *     out_t = y_t * silu(z_t)
  * The [B, L, D, N] tensors deltaA / deltaB_u of the reference are never materialised.
  * When `ckpt` is non-null the state at the start of every `chunk`-timestep block is written to
- * it (fp32, layout [batch, nchunks, dstate, dim], nchunks = ceil(seqlen/chunk); slot 0 is not
- * written) for use by mamba_scan_bwd; with a z gate the backward also needs `y_pre`.  When `h_last` is non-null the final state h_{L-1} is
+ * it (fp32, layout [batch, nchunks, ceil(dstate/4), dim, 4], nchunks = ceil(seqlen/chunk); slot 0 is
+ * not written; size from mamba_scan_ckpt_elems) for use by mamba_scan_bwd; with a z gate the backward also needs `y_pre`.  When `h_last` is non-null the final state h_{L-1} is
  * written to it ([batch, dim, dstate] fp32 — the decode step's `ssm_state` layout).
  * ------------------------------------------------------------------------------------------ */
 typedef struct MambaScanFwdArgs {

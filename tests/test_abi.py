@@ -73,6 +73,7 @@ def test_argument_validation_without_gpu(lib):
     n.rows, n.dim, n.dtype, n.resid_dtype = 4, 8, 0, 1
     assert lib.mamba_rmsnorm_fwd(C.byref(n), None) == -2
     assert lib.mamba_scan_ckpt_elems(2, 100, 64, 16, 16) == 2 * 7 * 16 * 64
+    assert lib.mamba_scan_ckpt_elems(1, 16, 32, 5, 16) == 1 * 1 * 8 * 32   # d_state padded to a multiple of 4
     assert lib.mamba_scan_bwd_workspace_bytes(0, 1, 1, 1) == 0
 
 
