@@ -320,7 +320,8 @@ def main():
     torch.manual_seed(0)
     model = train.new_model("mamba", layout="P").to(dev)
     adt = torch.bfloat16 if args.dtype == "bf16" else None
-    trainer = train.Trainer(model, autocast_dtype=adt, world_size=world, use_graph=not args.no_graph)
+    trainer = train.Trainer(model, autocast_dtype=adt, world_size=world, use_graph=not args.no_graph,
+                            overlap_allreduce=os.environ.get("MAMBA_B200_OVERLAP", "0") == "1")
 
     nb = 8
     host = [tuple(t.pin_memory() for t in synthetic.batch(B, T, seed=1000 * rank + i)) for i in range(nb)]

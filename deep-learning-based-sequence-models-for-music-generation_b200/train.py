@@ -284,7 +284,8 @@ class Trainer:
         torch.cuda.current_stream(self.device).wait_stream(s)
         torch.cuda.synchronize(self.device)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        mode = os.environ.get("MAMBA_B200_CAPTURE_MODE", "global")
+        with torch.cuda.graph(self.graph, capture_error_mode=mode):
             self._step_body()
         with torch.no_grad():
             for p, q in zip(self.model.parameters(), saved):
