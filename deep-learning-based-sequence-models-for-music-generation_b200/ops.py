@@ -84,10 +84,11 @@ def _call(name, a, dev):
 # selective scan
 # ------------------------------------------------------------------------------------------------
 def _scan_fwd_raw(u, delta, A, B, C, D, z, delta_bias, delta_softplus, ckpt, chunk, h_init=None, h_last=None,
-                  variant=0, y_pre=None):
+                  variant=0, y_pre=None, out=None):
     Bsz, L, Dm = u.shape
     N = A.shape[1]
-    out = torch.empty((Bsz, L, Dm), dtype=u.dtype, device=u.device)
+    if out is None:
+        out = torch.empty((Bsz, L, Dm), dtype=u.dtype, device=u.device)
     a = ScanFwdArgs()
     a.struct_size = ct.sizeof(ScanFwdArgs)
     a.dtype = _dtype_code(u)

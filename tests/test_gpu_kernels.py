@@ -426,3 +426,33 @@ def test_linear_step_matches_matmul(cfg, dtypes):
     y2 = ops.linear_step(x.cuda(), w.cuda(), None)
     assert_close(y2.float().cpu() + bias.float(), ref, 1e-4 if tx == torch.float32 else RTOL16,
                  1e-5 if tx == torch.float32 else FLOOR16, what="linear_step no bias")
+
+
+@pytest.mark.parametrize("shape", [(2, 37, 40, 5), (1, 50, 36, 48), (2, 33, 64, 16)])
+def test_scan_forward_writes_stay_inside_their_buffers(shape):
+    """Guard bands instead of a memory checker (compute-sanitizer is closed on this pool): every output of the
+    forward (out, checkpoints, pre-gate output, final state) lives inside a sentinel-filled arena at ragged shapes;
+    the sentinels around them must survive."""
+    from mamba_b200 import ops
+    from mamba_b200._lib import lib
+    B, L, D, N = shape
+    t = {k: v.cuda() for k, v in scan_inputs(B, L, D, N, seed=12).items()}
+    SENT = 12345.0
+    pad = 256
+
+    def arena(numel):
+        a = torch.full((numel + 2 * pad,), SENT, device="cuda")
+        return a, a[pad:pad + numel]
+
+    n_ck = lib().mamba_scan_ckpt_elems(B, L, D, N, 16)
+    arenas = {k: arena(n) for k, n in (("out", B * L * D), ("ckpt", n_ck), ("ypre", B * L * D), ("hlast", B * D * N))}
+    out = arenas["out"][1].view(B, L, D)
+    ops._scan_fwd_raw(t["u"], t["delta_raw"], t["A"], t["B"], t["C"], t["D"], t["z"], t["bias"], True,
+                      arenas["ckpt"][1], 16, h_last=arenas["hlast"][1].view(B, D, N), y_pre=arenas["ypre"][1].view(B, L, D),
+                      out=out)
+    torch.cuda.synchronize()
+    for k, (a, inner) in arenas.items():
+        assert bool((a[:pad] == SENT).all()) and bool((a[-pad:] == SENT).all()), f"{k}: write outside the buffer"
+    assert bool((out != SENT).all())
+    ref = _oracle_scan({k: v.cpu() for k, v in t.items()})
+    assert_close(out, ref, RTOL32, what=f"guarded scan fwd {shape}")
