@@ -12,12 +12,14 @@
 // paced by the MUFU pipe with the FMA pipe and the issue slots close behind; its HBM traffic is ~10x smaller
 // than that.  Organisation (same producer/consumer scheme as scan_fwd.cu):
 //   * one CTA owns (batch b, 32 channels); chunks are walked from the end of the sequence to the start.
-//   * SCAN warps: each thread owns a 4-channel x NPER-state register tile (a warp is 8 channel-lanes x 4
-//     state-lanes; warps tile the state axis).  Recompute: h_t for the 16 steps of the chunk -> shared memory
-//     (thread-private, conflict-free float4).  Reverse sweep: all arithmetic in packed fp32x2 (FFMA2/FMUL2) on
-//     channel pairs; a_t*h_{t-1} is obtained as h_t - delta*u*B so h_{t-1} is never re-read.  Sums over states
-//     (d_delta, d_u) are 2 butterfly steps across the state-lanes + one per-warp partial in shared memory, sums
-//     over channels (dB, dC) 3 butterfly steps across the channel-lanes.
+//   * SCAN warps: lane <-> channel, each thread owns NPER states of its channel (warps tile the state axis), so
+//     the per-channel operands are 4-byte shared loads (one wavefront per warp) and B / C are warp broadcasts.
+//     Recompute: h_t of the EVEN steps of the chunk -> shared memory (thread-private float4; odd steps are
+//     rebuilt in the reverse sweep).  Reverse sweep: all arithmetic in packed fp32x2 (FFMA2/FMUL2) on state
+//     pairs; a_t*h_{t-1} is h_t - delta*u*B on even steps and a_t*h_even on odd ones, so h_{t-1} is never
+//     re-read.  Sums over states (d_delta, d_u) finish inside the thread (+ one per-warp partial in shared
+//     memory); sums over the 32 channels (dB, dC) are a reduce-scatter across the lanes (2*NPER shuffles for
+//     2*NPER values instead of 5 per value).
 //   * HELPER warps (4): cp.async loads one chunk ahead, pre-pass (softplus(delta+bias), delta*u,
 //     dy = dout*silu(z)), post-pass (finish d_delta (softplus'), d_u (+D*dy), dz from the saved pre-gate output,
 //     accumulate dD / d_bias, 128-bit stores, per-CTA dB/dC partial -> workspace).
@@ -78,8 +80,8 @@ __device__ __forceinline__ float2 shfl_xor2(float2 v, int m) {
 // v[0..CNT); on exit v[0..CNT/2) holds the pair-sums of the lower half on lanes with the MASK bit clear and of the
 // upper half on lanes with it set.  CNT/2 shuffles instead of CNT (the selects run on the idle ALU pipe); the
 // shuffle/shared-memory pipe is the scarce one in this kernel.  With CNT == 1 it is a plain butterfly step.
-template <int CNT, int MASK>
-__device__ __forceinline__ void reduce_scatter_step(float (&v)[8], bool hi) {
+template <int CNT, int MASK, int LEN>
+__device__ __forceinline__ void reduce_scatter_step(float (&v)[LEN], bool hi) {
   if constexpr (CNT >= 2) {
     constexpr int H = CNT / 2;
 #pragma unroll
@@ -97,7 +99,7 @@ __device__ __forceinline__ void reduce_scatter_step(float (&v)[8], bool hi) {
 //   RAW ring slot (cp.async targets, element type T): u, delta, z, dout, ypre [CK][32];  B, C [CK][NPT]
 //   WORK slot (two): wdl, wdu, wdy fp32 [CK][32];  (bf16 I/O only) Bf, Cf fp32 [CK][NPT];
 //                    pg, pS [NW][CK][32] (per-warp partial sums over states);  redB, redC [CK][NPT]
-//   hs: float4 [CK/2][NPER][scan threads]  (h_t of the even steps of the chunk, 4 channels per float4, thread-private)
+//   hs: float4 [CK/2][NPER/4][scan threads]  (h_t of the even steps of the chunk, 4 states per float4, thread-private)
 template <typename T, int kCK>
 struct BwdLayout {
   int raw_u, raw_dl, raw_z, raw_do, raw_yp, raw_B, raw_C, raw_bytes;
@@ -124,7 +126,7 @@ struct BwdLayout {
     w_rB = o, o += kCK * NPT * 4;
     w_rC = o, o += kCK * NPT * 4;
     work_bytes = (o + 127) & ~127;
-    hs_bytes = (kCK / 2) * NPER * NW * 32 * 16;  // even steps only
+    hs_bytes = (kCK / 2) * (NPER / 4) * NW * 32 * 16;  // even steps only, one float4 per 4 states and thread
   }
 };
 
@@ -132,7 +134,7 @@ template <typename T, int NPER, int NW, int kCK>
 __global__ void __launch_bounds__((NW + kBHelperWarps) * 32, 1) scan_bwd_kernel(const ScanBwdParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  constexpr int NPT = ((NW * 4 * NPER + 7) / 8) * 8;  // padded d_state of the shared tiles
+  constexpr int NPT = ((NW * NPER + 7) / 8) * 8;  // padded d_state of the shared tiles
   const int b = blockIdx.y, tile = blockIdx.x;
   const int d0 = tile * kBD;
   const int dvalid = min(kBD, p.D - d0);
@@ -148,50 +150,38 @@ __global__ void __launch_bounds__((NW + kBHelperWarps) * 32, 1) scan_bwd_kernel(
 
   if (warp < NW) {
     // ========================================= SCAN WARPS ===============================================
-    const int ld = lane & 7, ln = lane >> 3;
-    const int nbase = (warp * 4 + ln) * NPER;  // first state of this thread
-    const int dl0 = 4 * ld;                    // first (tile-local) channel of this thread
-    float2 A2[2][NPER], dAacc[2][NPER], dhc[2][NPER];
+    // lane <-> channel (32 channels), this warp's slice of NPER states in registers, packed in pairs along n.
+    // Per-channel operands (delta, delta*u, dy) are then ONE 4-byte shared load per lane (a single wavefront per
+    // warp instead of four for a 16-byte load), B / C are full-warp broadcasts, sums over states stay inside the
+    // thread, and only the sums over channels (dB, dC) cross lanes.
+    constexpr int NQ = NPER / 4;   // float4 groups of states per thread
+    constexpr int NP = NPER / 2;   // state pairs per thread
+    const int n0 = warp * NPER;    // first state of this thread
+    const int d = d0 + lane;
+    float2 A2[NP], dAacc[NP], dhc[NP];
 #pragma unroll
     for (int j = 0; j < NPER; ++j) {
-      float a[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int d = d0 + dl0 + i, n = nbase + j;
-        a[i] = (d < p.D && n < p.N) ? p.A[(int64_t)d * p.N + n] * kLog2e : 0.f;
-      }
-      A2[0][j] = make_float2(a[0], a[1]), A2[1][j] = make_float2(a[2], a[3]);
-      dAacc[0][j] = dAacc[1][j] = make_float2(0.f, 0.f);
-      dhc[0][j] = dhc[1][j] = make_float2(0.f, 0.f);
+      const int n = n0 + j;
+      const float a = (d < p.D && n < p.N) ? p.A[(int64_t)d * p.N + n] * kLog2e : 0.f;
+      if (j & 1) A2[j / 2].y = a;
+      else A2[j / 2].x = a;
     }
-    // chunk-start state of chunk c from the forward's checkpoints (zero for chunk 0)
-    // checkpoint layout [B][nck][ceil(N/4)][D][4] (scan_fwd.cu): the NPER states of one channel are contiguous
+#pragma unroll
+    for (int q = 0; q < NP; ++q) dAacc[q] = dhc[q] = make_float2(0.f, 0.f);
+    // checkpoint layout [B][nck][ceil(N/4)][D][4] (scan_fwd.cu): 16 bytes per lane, 512 contiguous bytes per warp
     const int N4 = (p.N + 3) >> 2;
-    auto load_ckpt = [&](int c, float2 (&h)[2][NPER]) {
-      float v[4][NPER];
+    auto load_ckpt = [&](int c, float2 (&h)[NP]) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-#pragma unroll
-        for (int j = 0; j < NPER; ++j) v[i][j] = 0.f;
-        if (c > 0 && dl0 + i < dvalid && nbase < p.N) {
-          const float* ck = p.ckpt + ((((int64_t)b * nck + c) * N4 + (nbase >> 2)) * p.D + d0 + dl0 + i) * 4 + (nbase & 3);
-          if constexpr (NPER == 4) {
-            const float4 t4 = __ldg(reinterpret_cast<const float4*>(ck));
-            v[i][0] = t4.x, v[i][1] = t4.y, v[i][2] = t4.z, v[i][3] = t4.w;
-          } else if constexpr (NPER == 2) {
-            const float2 t2 = __ldg(reinterpret_cast<const float2*>(ck));
-            v[i][0] = t2.x, v[i][1] = t2.y;
-          } else {
-            v[i][0] = __ldg(ck);
-          }
-        }
+      for (int q = 0; q < NQ; ++q) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c > 0 && d < p.D && n0 + 4 * q < p.N)
+          v = __ldg(reinterpret_cast<const float4*>(p.ckpt) + (((int64_t)b * nck + c) * N4 + (n0 >> 2) + q) * p.D + d);
+        h[2 * q] = make_float2(v.x, v.y), h[2 * q + 1] = make_float2(v.z, v.w);
       }
-#pragma unroll
-      for (int j = 0; j < NPER; ++j) h[0][j] = make_float2(v[0][j], v[1][j]), h[1][j] = make_float2(v[2][j], v[3][j]);
     };
-    float2 hnext[2][NPER];
+    float2 hnext[NP];
     load_ckpt(nck - 1, hnext);
-    float4* const hst = hs + tid;  // + (t * NPER + j) * nscan_threads
+    float4* const hst = hs + tid;  // + (tp * NQ + q) * nscan_threads
 
     int rslot = 0;
     for (int it = 0; it < nck; ++it) {
@@ -199,43 +189,38 @@ __global__ void __launch_bounds__((NW + kBHelperWarps) * 32, 1) scan_bwd_kernel(
       const int ws = it & 1;
       unsigned char* wbase = work_base + (size_t)ws * lay.work_bytes;
       unsigned char* rbase = raw_base + (size_t)rslot * lay.raw_bytes;
-      const float* wdl = reinterpret_cast<const float*>(wbase + lay.w_dl) + dl0;
-      const float* wdu = reinterpret_cast<const float*>(wbase + lay.w_du) + dl0;
-      const float* wdy = reinterpret_cast<const float*>(wbase + lay.w_dy) + dl0;
+      const float* wdl = reinterpret_cast<const float*>(wbase + lay.w_dl) + lane;
+      const float* wdu = reinterpret_cast<const float*>(wbase + lay.w_du) + lane;
+      const float* wdy = reinterpret_cast<const float*>(wbase + lay.w_dy) + lane;
       const float* Bf = (sizeof(T) == 4 ? reinterpret_cast<const float*>(rbase + lay.raw_B)
-                                        : reinterpret_cast<const float*>(wbase + lay.w_Bf)) + nbase;
+                                        : reinterpret_cast<const float*>(wbase + lay.w_Bf)) + n0;
       const float* Cf = (sizeof(T) == 4 ? reinterpret_cast<const float*>(rbase + lay.raw_C)
-                                        : reinterpret_cast<const float*>(wbase + lay.w_Cf)) + nbase;
-      float* pg = reinterpret_cast<float*>(wbase + lay.w_pg) + (warp * kCK) * kBD + dl0;
-      float* pS = reinterpret_cast<float*>(wbase + lay.w_pS) + (warp * kCK) * kBD + dl0;
-      float* redB = reinterpret_cast<float*>(wbase + lay.w_rB) + nbase;
-      float* redC = reinterpret_cast<float*>(wbase + lay.w_rC) + nbase;
+                                        : reinterpret_cast<const float*>(wbase + lay.w_Cf)) + n0;
+      float* pg = reinterpret_cast<float*>(wbase + lay.w_pg) + (warp * kCK) * kBD + lane;
+      float* pS = reinterpret_cast<float*>(wbase + lay.w_pS) + (warp * kCK) * kBD + lane;
+      float* redB = reinterpret_cast<float*>(wbase + lay.w_rB) + n0;
+      float* redC = reinterpret_cast<float*>(wbase + lay.w_rC) + n0;
 
-      float2 h[2][NPER];
+      float2 h[NP];
 #pragma unroll
-      for (int j = 0; j < NPER; ++j) h[0][j] = hnext[0][j], h[1][j] = hnext[1][j];
+      for (int q = 0; q < NP; ++q) h[q] = hnext[q];
       bar_sync(1 + ws, bar_count);  // chunk c prepared
 
-      // ---- forward recompute: h_t for every step of the chunk -> shared memory ---------------------------
+      // ---- forward recompute: h_t of the EVEN steps of the chunk -> shared memory --------------------------
 #pragma unroll 4
       for (int t = 0; t < kCK; ++t) {
-        const float4 dl4 = *reinterpret_cast<const float4*>(wdl + t * kBD);
-        const float4 du4 = *reinterpret_cast<const float4*>(wdu + t * kBD);
-        const float2 dlp[2] = {make_float2(dl4.x, dl4.y), make_float2(dl4.z, dl4.w)};
-        const float2 dup[2] = {make_float2(du4.x, du4.y), make_float2(du4.z, du4.w)};
-        float Bv[NPER];
-        lds_vec<NPER>(Bv, Bf + t * NPT);
+        const float dl = wdl[t * kBD], du = wdu[t * kBD];
+        const float2 dl2 = make_float2(dl, dl), du2 = make_float2(du, du);
 #pragma unroll
-        for (int j = 0; j < NPER; ++j) {
-          const float2 Bb = make_float2(Bv[j], Bv[j]);
-#pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            const float2 g = __fmul2_rn(dlp[q], A2[q][j]);
-            const float2 a = make_float2(ex2_approx(g.x), ex2_approx(g.y));
-            h[q][j] = __ffma2_rn(a, h[q][j], __fmul2_rn(dup[q], Bb));
-          }
+        for (int q = 0; q < NQ; ++q) {
+          const float4 b4 = *reinterpret_cast<const float4*>(Bf + t * NPT + 4 * q);
+          const float2 g0 = __fmul2_rn(dl2, A2[2 * q]), g1 = __fmul2_rn(dl2, A2[2 * q + 1]);
+          const float2 a0 = make_float2(ex2_approx(g0.x), ex2_approx(g0.y));
+          const float2 a1 = make_float2(ex2_approx(g1.x), ex2_approx(g1.y));
+          h[2 * q] = __ffma2_rn(a0, h[2 * q], __fmul2_rn(du2, make_float2(b4.x, b4.y)));
+          h[2 * q + 1] = __ffma2_rn(a1, h[2 * q + 1], __fmul2_rn(du2, make_float2(b4.z, b4.w)));
           if ((t & 1) == 0)  // odd steps are rebuilt in the reverse sweep from the even one before them
-            hst[((t >> 1) * NPER + j) * nscan_threads] = make_float4(h[0][j].x, h[0][j].y, h[1][j].x, h[1][j].y);
+            hst[((t >> 1) * NQ + q) * nscan_threads] = make_float4(h[2 * q].x, h[2 * q].y, h[2 * q + 1].x, h[2 * q + 1].y);
         }
       }
       // prefetch the next chunk's start state: its latency hides behind the reverse sweep
@@ -244,98 +229,105 @@ __global__ void __launch_bounds__((NW + kBHelperWarps) * 32, 1) scan_bwd_kernel(
       // ---- reverse sweep: adjoint recurrence ------------------------------------------------------------------
       // Steps are taken in (odd, even) pairs: only h of the even step is in shared memory; the odd step's state
       // is h_odd = a_odd * h_even + delta*u*B, whose first term is exactly the a_t * h_{t-1} the gradient needs.
-      auto rev_step = [&](const int t, const float2 (&hprev)[2][NPER], const bool odd) {
-        const float4 dl4 = *reinterpret_cast<const float4*>(wdl + t * kBD);
-        const float4 du4 = *reinterpret_cast<const float4*>(wdu + t * kBD);
-        const float4 dy4 = *reinterpret_cast<const float4*>(wdy + t * kBD);
-        const float2 dlp[2] = {make_float2(dl4.x, dl4.y), make_float2(dl4.z, dl4.w)};
-        const float2 dup[2] = {make_float2(du4.x, du4.y), make_float2(du4.z, du4.w)};
-        const float2 dyp[2] = {make_float2(dy4.x, dy4.y), make_float2(dy4.z, dy4.w)};
-        float Bv[NPER], Cv[NPER];
-        lds_vec<NPER>(Bv, Bf + t * NPT);
-        lds_vec<NPER>(Cv, Cf + t * NPT);
-        float2 gs[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
-        float2 S[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
-        float red[8];  // (dB_j, dC_j) partials of this thread's 4 channels, j = 0..NPER-1
+      // Each step is split into load / compute / store so that the shared loads of the second step of a pair sit
+      // BEFORE the shared stores of the first in program order (ptxas does not move a load above a store it cannot
+      // disambiguate) and can overlap the first step's arithmetic.
+      struct RevOps {
+        float dl, du, dy;
+        float4 B[NQ], C[NQ];
+      };
+      struct RevOut {
+        float g, S, red;
+      };
+      auto rev_load = [&](const int t, RevOps& o) {
+        o.dl = wdl[t * kBD], o.du = wdu[t * kBD], o.dy = wdy[t * kBD];
 #pragma unroll
-        for (int j = 0; j < NPER; ++j) {
-          const float2 Bb = make_float2(Bv[j], Bv[j]), Cb = make_float2(Cv[j], Cv[j]);
-          float2 db2 = make_float2(0.f, 0.f), dc2 = make_float2(0.f, 0.f);
-#pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            const float2 ga = __fmul2_rn(dlp[q], A2[q][j]);
-            const float2 a = make_float2(ex2_approx(ga.x), ex2_approx(ga.y));
-            const float2 bu = __fmul2_rn(dup[q], Bb);
-            float2 hm, hc;  // hm = a_t * h_{t-1}, hc = h_t
-            if (odd) {
-              hm = __fmul2_rn(a, hprev[q][j]);
-              hc = __fadd2_rn(hm, bu);
-            } else {
-              hc = hprev[q][j];
-              hm = __ffma2_rn(make_float2(-dup[q].x, -dup[q].y), Bb, hc);
-            }
-            const float2 dh = __ffma2_rn(Cb, dyp[q], dhc[q][j]);
-            dc2 = __ffma2_rn(dyp[q], hc, dc2);
-            const float2 g = __fmul2_rn(dh, hm);  // dL/d(delta*A) for these two (d, n)
-            gs[q] = __ffma2_rn(g, A2[q][j], gs[q]);
-            dAacc[q][j] = __ffma2_rn(g, dlp[q], dAacc[q][j]);
-            S[q] = __ffma2_rn(dh, Bb, S[q]);
-            db2 = __ffma2_rn(dh, dup[q], db2);
-            dhc[q][j] = __fmul2_rn(a, dh);
-          }
-          red[2 * j] = db2.x + db2.y, red[2 * j + 1] = dc2.x + dc2.y;
-        }
-        // sums over this warp's 4 state-lanes (lane bits 4, 3): reduce-scatter of the 8 values
-        // (g of 4 channels, S of 4 channels); every lane ends up with 2 of them
-        {
-          float v[8] = {gs[0].x, gs[0].y, gs[1].x, gs[1].y, S[0].x, S[0].y, S[1].x, S[1].y};
-          reduce_scatter_step<8, 16>(v, lane & 16);
-          reduce_scatter_step<4, 8>(v, lane & 8);
-          float* dst = ((lane & 16) ? pS : pg) + t * kBD + ((lane & 8) ? 2 : 0);
-          *reinterpret_cast<float2*>(dst) = make_float2(v[0], v[1]);
-        }
-        // sums over the warp's 8 channel-lanes (lane bits 2, 1, 0): reduce-scatter of the 2*NPER values
-        {
-          reduce_scatter_step<2 * NPER, 4>(red, lane & 4);
-          reduce_scatter_step<(NPER >= 2 ? NPER : 1), 2>(red, lane & 2);
-          reduce_scatter_step<(NPER >= 4 ? NPER / 2 : 1), 1>(red, lane & 1);
-          // lane (b2 b1 b0) now holds value index idx of the original (dB_0, dC_0, dB_1, dC_1, ...) list
-          int idx;
-          bool writer = true;
-          if constexpr (NPER == 4) {
-            idx = lane & 7;
-          } else if constexpr (NPER == 2) {
-            idx = (lane >> 1) & 3, writer = (lane & 1) == 0;
-          } else {
-            idx = (lane >> 2) & 1, writer = (lane & 3) == 0;
-          }
-          if (writer) ((idx & 1) ? redC : redB)[t * NPT + (idx >> 1)] = red[0];
+        for (int q = 0; q < NQ; ++q) {
+          o.B[q] = *reinterpret_cast<const float4*>(Bf + t * NPT + 4 * q);
+          o.C[q] = *reinterpret_cast<const float4*>(Cf + t * NPT + 4 * q);
         }
       };
-#pragma unroll 2
-      for (int tp = kCK / 2 - 1; tp >= 0; --tp) {
-        float2 he[2][NPER];
+      auto rev_compute = [&](const RevOps& o, const float2 (&hprev)[NP], const bool odd, RevOut& out) {
+        const float2 dl2 = make_float2(o.dl, o.dl), du2 = make_float2(o.du, o.du), dy2 = make_float2(o.dy, o.dy);
+        const float2 ndu2 = make_float2(-o.du, -o.du);
+        float2 gs2 = make_float2(0.f, 0.f), S2 = make_float2(0.f, 0.f);
+        float red[2 * NPER];  // dB_0..dB_{NPER-1}, dC_0..dC_{NPER-1} of this lane's channel
 #pragma unroll
-        for (int j = 0; j < NPER; ++j) {
-          const float4 h4 = hst[(tp * NPER + j) * nscan_threads];
-          he[0][j] = make_float2(h4.x, h4.y), he[1][j] = make_float2(h4.z, h4.w);
+        for (int q = 0; q < NQ; ++q) {
+          const float2 Bp[2] = {make_float2(o.B[q].x, o.B[q].y), make_float2(o.B[q].z, o.B[q].w)};
+          const float2 Cp[2] = {make_float2(o.C[q].x, o.C[q].y), make_float2(o.C[q].z, o.C[q].w)};
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            const int k = 2 * q + r;  // state pair index
+            const float2 ga = __fmul2_rn(dl2, A2[k]);
+            const float2 a = make_float2(ex2_approx(ga.x), ex2_approx(ga.y));
+            float2 hm, hc;  // hm = a_t * h_{t-1}, hc = h_t
+            if (odd) {
+              hm = __fmul2_rn(a, hprev[k]);
+              hc = __ffma2_rn(du2, Bp[r], hm);
+            } else {
+              hc = hprev[k];
+              hm = __ffma2_rn(ndu2, Bp[r], hc);
+            }
+            const float2 dh = __ffma2_rn(Cp[r], dy2, dhc[k]);
+            const float2 dc = __fmul2_rn(dy2, hc);
+            const float2 db = __fmul2_rn(dh, du2);
+            const float2 g = __fmul2_rn(dh, hm);  // dL/d(delta*A) for these two states
+            gs2 = __ffma2_rn(g, A2[k], gs2);
+            dAacc[k] = __ffma2_rn(g, dl2, dAacc[k]);
+            S2 = __ffma2_rn(dh, Bp[r], S2);
+            dhc[k] = __fmul2_rn(a, dh);
+            red[2 * k] = db.x, red[2 * k + 1] = db.y;
+            red[NPER + 2 * k] = dc.x, red[NPER + 2 * k + 1] = dc.y;
+          }
         }
-        rev_step(2 * tp + 1, he, true);
-        rev_step(2 * tp, he, false);
+        // sums over states are complete inside the thread
+        out.g = gs2.x + gs2.y, out.S = S2.x + S2.y;
+        // sums over the 32 channels of the warp: reduce-scatter of the 2*NPER values, then plain butterflies
+        constexpr int V = 2 * NPER;
+        reduce_scatter_step<V, 16>(red, lane & 16);
+        reduce_scatter_step<(V >= 2 ? V / 2 : 1), 8>(red, lane & 8);
+        reduce_scatter_step<(V >= 4 ? V / 4 : 1), 4>(red, lane & 4);
+        reduce_scatter_step<(V >= 8 ? V / 8 : 1), 2>(red, lane & 2);
+        reduce_scatter_step<(V >= 16 ? V / 16 : 1), 1>(red, lane & 1);
+        out.red = red[0];
+      };
+      // V = 32: every lane holds one value (index = lane); V = 16: index = lane >> 1; V = 8: index = lane >> 2
+      constexpr int SH = 2 * NPER >= 32 ? 0 : (2 * NPER == 16 ? 1 : 2);
+      const int ridx = lane >> SH;
+      const bool rwriter = (lane & ((1 << SH) - 1)) == 0;
+      float* const rdst = (ridx >= NPER ? redC : redB) + (ridx % NPER);
+      auto rev_store = [&](const int t, const RevOut& out) {
+        pg[t * kBD] = out.g;
+        pS[t * kBD] = out.S;
+        if (rwriter) rdst[t * NPT] = out.red;
+      };
+#pragma unroll 1
+      for (int tp = kCK / 2 - 1; tp >= 0; --tp) {
+        float2 he[NP];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          const float4 h4 = hst[(tp * NQ + q) * nscan_threads];
+          he[2 * q] = make_float2(h4.x, h4.y), he[2 * q + 1] = make_float2(h4.z, h4.w);
+        }
+        RevOps o1, o0;
+        RevOut r1, r0;
+        rev_load(2 * tp + 1, o1);
+        rev_load(2 * tp, o0);
+        rev_compute(o1, he, true, r1);
+        rev_compute(o0, he, false, r0);
+        rev_store(2 * tp + 1, r1);
+        rev_store(2 * tp, r0);
       }
       bar_arrive(3 + ws, bar_count);  // chunk c swept
       rslot = (rslot + 1 == kBRing) ? 0 : rslot + 1;
     }
     // ---- epilogue: dA partial of this batch element -----------------------------------------------------------
+    if (d < p.D) {
 #pragma unroll
-    for (int j = 0; j < NPER; ++j) {
-      const int n = nbase + j;
-      if (n < p.N) {
-        float* dst = p.ws_dA + ((int64_t)b * p.N + n) * p.D + d0 + dl0;
-        const float v[4] = {dAacc[0][j].x, dAacc[0][j].y, dAacc[1][j].x, dAacc[1][j].y};
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (dl0 + i < dvalid) dst[i] = v[i];
+      for (int j = 0; j < NPER; ++j) {
+        const int n = n0 + j;
+        if (n < p.N) p.ws_dA[((int64_t)b * p.N + n) * p.D + d] = (j & 1) ? dAacc[j / 2].y : dAacc[j / 2].x;
       }
     }
     return;
@@ -672,16 +664,16 @@ static int bwd_dispatch_ck(const ScanBwdParams& p, cudaStream_t stream) {
 
 template <typename T>
 static int bwd_dispatch(ScanBwdParams& p, int nper, cudaStream_t stream) {
-  p.NW = ceil_div(p.N, 4 * nper);
+  p.NW = ceil_div(p.N, nper);
   if (p.NW > kBMaxWarps) return set_error(MAMBA_ESIZE, "scan_bwd: d_state %d too large (max %d)", p.N, kBMaxWarps * 16);
   p.NW = p.NW <= 2 ? p.NW : (p.NW <= 4 ? 4 : 8);  // instantiated warp counts
-  p.NPT = (p.NW * 4 * nper + 7) & ~7;
+  p.NPT = (p.NW * nper + 7) & ~7;
   switch (nper) {
-    case 1: return bwd_dispatch_ck<T, 1>(p, stream);
-    case 2: return bwd_dispatch_ck<T, 2>(p, stream);
     case 4: return bwd_dispatch_ck<T, 4>(p, stream);
+    case 8: return bwd_dispatch_ck<T, 8>(p, stream);
+    case 16: return bwd_dispatch_ck<T, 16>(p, stream);
   }
-  return set_error(MAMBA_EINVAL, "scan_bwd: variant must be 0, 1, 2 or 4 (got %d)", nper);
+  return set_error(MAMBA_EINVAL, "scan_bwd: variant must be 0, 4, 8 or 16 (got %d)", nper);
 }
 
 static bool bvec_ok(const void* ptr, int64_t bs, int64_t ls, size_t elt) {
@@ -756,8 +748,8 @@ extern "C" int mamba_scan_bwd(const MambaScanBwdArgs* a, void* stream) {
   p.vec_ck = a->ckpt && aligned16(a->ckpt) && (p.D % 4 == 0);
 
   int nper = a->variant;
-  if (nper == 0) nper = p.N <= 16 ? 1 : (p.N <= 64 ? 2 : 4);  // measured: 8 scan warps of 4x2 tiles beat 4 of 4x4 at N = 64
-  while (nper < 4 && ceil_div(p.N, 4 * nper) > kBMaxWarps) nper *= 2;
+  if (nper == 0) nper = p.N <= 32 ? 4 : 8;  // states per thread: up to 8 scan warps
+  while (nper < 16 && ceil_div(p.N, nper) > kBMaxWarps) nper *= 2;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   return a->dtype == MAMBA_F32 ? bwd_dispatch<float>(p, nper, st) : bwd_dispatch<__nv_bfloat16>(p, nper, st);
 }
