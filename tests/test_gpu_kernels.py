@@ -161,6 +161,31 @@ def test_scan_bf16_io():
         assert_close(g[k].grad, c[k].grad, RTOL16, FLOOR16, what=f"scan bwd bf16 d{k}")
 
 
+@pytest.mark.parametrize("variant", [1, 8])       # 1: tensor-pipe channel sums, 8: lane<->channel kernel
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(2, 100, 72, 64), (1, 41, 104, 32)])  # ragged channel tiles, L % chunk != 0
+def test_scan_backward_variants_at_repo_d_state(variant, dtype, shape):
+    """Both backward kernels at d_state 64 / 32, fp32 (split-tf32 column sums) and bf16 I/O (plain tf32)."""
+    from mamba_b200 import ops
+    B, L, D, N = shape
+    t = scan_inputs(B, L, D, N, seed=11, dtype=dtype)
+    dout = torch.randn(B, L, D, generator=torch.Generator().manual_seed(5)).to(dtype)
+    c = _leafs(t, "cpu")
+    ref = _oracle_scan(c)
+    ref.backward(dout.float())
+    g = _leafs(t, "cuda")
+    ops.SCAN_BWD_VARIANT = variant
+    try:
+        out = ops.selective_scan_fn(g["u"], g["delta_raw"], g["A"], g["B"], g["C"], g["D"], z=g["z"],
+                                    delta_bias=g["bias"], delta_softplus=True)
+        out.backward(dout.cuda())
+    finally:
+        ops.SCAN_BWD_VARIANT = 0
+    rtol, floor = (RTOL32, 1e-5) if dtype == torch.float32 else (RTOL16, FLOOR16)
+    for k in c:
+        assert_close(g[k].grad, c[k].grad, rtol, floor, what=f"scan bwd variant {variant} {dtype} d{k} {shape}")
+
+
 def test_scan_state_carry_composes_at_full_size():
     """Size-independent property at BASELINE's long-context shape (L=8192, N=16, D=2048): scanning the whole
     sequence equals scanning two halves with the state carried (h_init), and equals the oracle on a slice."""
