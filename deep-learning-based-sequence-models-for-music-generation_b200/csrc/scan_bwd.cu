@@ -24,101 +24,9 @@
 //     dy = dout*silu(z)), post-pass (finish d_delta (softplus'), d_u (+D*dy), dz from the saved pre-gate output,
 //     accumulate dD / d_bias, 128-bit stores, per-CTA dB/dC partial -> workspace).
 //   * a finalize kernel reduces the per-CTA / per-batch partials in a fixed order (deterministic, no atomics).
-#include "common.cuh"
+#include "scan_bwd.cuh"
 
 namespace mb {
-
-constexpr int kBD = 32;        // channels per CTA
-constexpr int kBHelperWarps = 4;
-constexpr int kBHelperThreads = kBHelperWarps * 32;
-constexpr int kBMaxWarps = 8;  // scan warps per CTA
-constexpr int kBRing = 2;      // raw-tile ring depth (a chunk is >= 2 us of work at d_state 64)
-
-struct ScanBwdParams {
-  int B, L, D, N, NW, NPT, nck, ck, flags, ntiles;
-  const void *u, *delta, *Bm, *Cm, *z, *dout, *ypre;
-  int64_t u_bs, u_ls, delta_bs, delta_ls, B_bs, B_ls, C_bs, C_ls, z_bs, z_ls, dout_bs, dout_ls, ypre_bs, ypre_ls;
-  void *du, *ddelta, *dz, *dB, *dC;
-  int64_t du_bs, du_ls, ddelta_bs, ddelta_ls, dz_bs, dz_ls, dB_bs, dB_ls, dC_bs, dC_ls;
-  const float *A, *Dv, *dbias, *ckpt;
-  float *dA, *dD, *ddbias;
-  // workspace carve-up (fp32)
-  float *ws_dB, *ws_dC;  // [B][ntiles][L][N]
-  float *ws_dA;          // [B][N][D]
-  float *ws_dD, *ws_db;  // [B][D]
-  int vec_u, vec_delta, vec_z, vec_dout, vec_ypre, vec_B, vec_C, vec_ck, vec_du, vec_ddelta, vec_dz;
-};
-
-template <int NPER>
-__device__ __forceinline__ void lds_vec(float (&dst)[NPER], const float* src) {
-  if constexpr (NPER == 4) {
-    const float4 v = *reinterpret_cast<const float4*>(src);
-    dst[0] = v.x, dst[1] = v.y, dst[2] = v.z, dst[3] = v.w;
-  } else if constexpr (NPER == 2) {
-    const float2 v = *reinterpret_cast<const float2*>(src);
-    dst[0] = v.x, dst[1] = v.y;
-  } else {
-#pragma unroll
-    for (int j = 0; j < NPER; ++j) dst[j] = src[j];
-  }
-}
-template <int NPER>
-__device__ __forceinline__ void sts_vec(float* dst, const float (&v)[NPER]) {
-  if constexpr (NPER == 4) {
-    *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-  } else if constexpr (NPER == 2) {
-    *reinterpret_cast<float2*>(dst) = make_float2(v[0], v[1]);
-  } else {
-#pragma unroll
-    for (int j = 0; j < NPER; ++j) dst[j] = v[j];
-  }
-}
-__device__ __forceinline__ float2 shfl_xor2(float2 v, int m) {
-  return make_float2(__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m));
-}
-// One reduce-scatter step over the lane pair (lane, lane ^ MASK): on entry every lane holds CNT partial values
-// v[0..CNT); on exit v[0..CNT/2) holds the pair-sums of the lower half on lanes with the MASK bit clear and of the
-// upper half on lanes with it set.  CNT/2 shuffles instead of CNT (the selects run on the idle ALU pipe); the
-// shuffle/shared-memory pipe is the scarce one in this kernel.  With CNT == 1 it is a plain butterfly step.
-template <int CNT, int MASK, int LEN>
-__device__ __forceinline__ void reduce_scatter_step(float (&v)[LEN], bool hi) {
-  if constexpr (CNT >= 2) {
-    constexpr int H = CNT / 2;
-#pragma unroll
-    for (int i = 0; i < H; ++i) {
-      const float send = hi ? v[i] : v[i + H];
-      const float keep = hi ? v[i + H] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, MASK);
-    }
-  } else {
-    v[0] += __shfl_xor_sync(0xffffffffu, v[0], MASK);
-  }
-}
-
-// D[16x8] += A[16x8] * B[8x8] on the tensor pipe (legacy mma.sync, tf32 operands, fp32 accumulate).  Fragment
-// layout (g = lane >> 2, t = lane & 3): a0 = A[g][t], a1 = A[g+8][t], a2 = A[g][t+4], a3 = A[g+8][t+4];
-// b0 = B[t][g], b1 = B[t+4][g]; c0 = D[g][2t], c1 = D[g][2t+1], c2 = D[g+8][2t], c3 = D[g+8][2t+1].
-__device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b) {
-  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%8}, {%0,%1,%2,%3};"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b));
-}
-// Column sums over the 8 channels of a warp's octet: x0 / x1 are the (state 2i, state 2i+1) values of the thread's
-// first / second channel, `onehot` is 1.0f on the lanes whose g equals the step's column.  kSplit adds the
-// low-order term (x - tf32(x)) so that the sum is exact to ~2^-21 (fp32 I/O); without it the operands are
-// truncated to tf32 (rel. 2^-10, far inside the bf16 I/O tolerance).
-template <bool kSplit>
-__device__ __forceinline__ void mma_colsum(float (&c)[4], float2 x0, float2 x1, uint32_t onehot) {
-  const uint32_t a0 = __float_as_uint(x0.x), a1 = __float_as_uint(x0.y), a2 = __float_as_uint(x1.x), a3 = __float_as_uint(x1.y);
-  if constexpr (kSplit) {
-    const uint32_t h0 = a0 & 0xffffe000u, h1 = a1 & 0xffffe000u, h2 = a2 & 0xffffe000u, h3 = a3 & 0xffffe000u;
-    mma_tf32(c, h0, h1, h2, h3, onehot);
-    mma_tf32(c, __float_as_uint(x0.x - __uint_as_float(h0)), __float_as_uint(x0.y - __uint_as_float(h1)),
-             __float_as_uint(x1.x - __uint_as_float(h2)), __float_as_uint(x1.y - __uint_as_float(h3)), onehot);
-  } else {
-    mma_tf32(c, a0, a1, a2, a3, onehot);
-  }
-}
 
 // Shared-memory layout.
 //   RAW ring slot (cp.async targets, element type T): u, delta, z, dout, ypre [CK][32];  B, C [CK][NPT]
@@ -130,9 +38,7 @@ struct BwdLayout {
   int raw_u, raw_dl, raw_z, raw_do, raw_yp, raw_B, raw_C, raw_bytes;
   int w_dl, w_du, w_dy, w_Bf, w_Cf, w_pg, w_pS, w_rB, w_rC, work_bytes;
   int hs_bytes;
-  // mma = true (scan_bwd_kernel's kMma): pg/pS hold one partial per state half (NW/4), and w_rB holds the per-octet
-  // partials of dB|dC: [4 channel octets][CK][RS = 2*NPT + 4] (row stride == 4 mod 16 floats: conflict-free flushes)
-  __host__ __device__ BwdLayout(int NW, int NPT, int NPER, bool mma = false) {
+  __host__ __device__ BwdLayout(int NW, int NPT, int NPER) {
     int o = 0;
     raw_u = o, o += kCK * kBD * (int)sizeof(T);
     raw_dl = o, o += kCK * kBD * (int)sizeof(T);
@@ -148,17 +54,16 @@ struct BwdLayout {
     w_dy = o, o += kCK * kBD * 4;
     w_Bf = o, o += (sizeof(T) == 4 ? 0 : kCK * NPT * 4);
     w_Cf = o, o += (sizeof(T) == 4 ? 0 : kCK * NPT * 4);
-    const int npart = mma ? (NW >= 4 ? NW / 4 : 1) : NW;
-    w_pg = o, o += npart * kCK * kBD * 4;
-    w_pS = o, o += npart * kCK * kBD * 4;
-    w_rB = o, o += mma ? 4 * kCK * (2 * NPT + 4) * 4 : kCK * NPT * 4;
-    w_rC = o, o += mma ? 0 : kCK * NPT * 4;
+    w_pg = o, o += NW * kCK * kBD * 4;
+    w_pS = o, o += NW * kCK * kBD * 4;
+    w_rB = o, o += kCK * NPT * 4;
+    w_rC = o, o += kCK * NPT * 4;
     work_bytes = (o + 127) & ~127;
     hs_bytes = (kCK / 2) * (NPER / 4) * NW * 32 * 16;  // even steps only, one float4 per 4 states and thread
   }
 };
 
-template <typename T, int NPER, int NW, int kCK, bool kMma>
+template <typename T, int NPER, int NW, int kCK>
 __global__ void __launch_bounds__((NW + kBHelperWarps) * 32, 1) scan_bwd_kernel(const ScanBwdParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -166,9 +71,7 @@ __global__ void __launch_bounds__((NW + kBHelperWarps) * 32, 1) scan_bwd_kernel(
   const int b = blockIdx.y, tile = blockIdx.x;
   const int d0 = tile * kBD;
   const int dvalid = min(kBD, p.D - d0);
-  const BwdLayout<T, kCK> lay(NW, NPT, NPER, kMma);
-  constexpr int RS = 2 * NPT + 4;                  // kMma: row stride of the dB|dC octet partials
-  constexpr int NPART = kMma ? (NW >= 4 ? NW / 4 : 1) : NW;  // partials of the sums over states
+  const BwdLayout<T, kCK> lay(NW, NPT, NPER);
   unsigned char* const raw_base = smem;
   unsigned char* const work_base = smem + (size_t)kBRing * lay.raw_bytes;
   float4* const hs = reinterpret_cast<float4*>(work_base + (size_t)2 * lay.work_bytes);
@@ -178,195 +81,6 @@ __global__ void __launch_bounds__((NW + kBHelperWarps) * 32, 1) scan_bwd_kernel(
   const bool has_z = p.flags & MAMBA_FLAG_HAS_Z;
   // barrier ids: 1,2 = READY[work slot]; 3,4 = DONE[work slot]; 5 = helpers only.  Iteration i handles chunk nck-1-i.
 
-  if constexpr (kMma) {
-   if (warp < NW) {
-    // ================================= SCAN WARPS (tensor-pipe reductions) ===================================
-    // warp = (channel octet cg, state half sh); lane = (g = lane >> 2: quad of 4 states, t = lane & 3: channel pair).
-    // A thread owns 2 channels x 4 states.  The sums over channels (dB, dC) are done by the tensor pipe: the
-    // thread's products ARE an mma.m16n8k8 A-fragment (rows = states, k = the octet's 8 channels), multiplied by a
-    // one-hot B-fragment that routes the column sum to the accumulator column of the current timestep, so eight
-    // steps accumulate in registers and are flushed with four 16-byte stores.  Only the sums over states cross
-    // lanes (4 values over the 8 g-lanes: 4 shuffles).
-    const int t4 = lane & 3, g = lane >> 2;
-    const int cg = warp & 3, sh = warp >> 2;
-    const int cl = 8 * cg + 2 * t4;  // first (tile-local) channel of this thread
-    const int n0 = 32 * sh + 4 * g;  // first state of this thread
-    const int d = d0 + cl;
-    float2 A2[2][2], dAacc[2][2], dhc[2][2];
-#pragma unroll
-    for (int ch = 0; ch < 2; ++ch)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float a = (d + ch < p.D && n0 + j < p.N) ? p.A[(int64_t)(d + ch) * p.N + n0 + j] * kLog2e : 0.f;
-        if (j & 1) A2[ch][j / 2].y = a;
-        else A2[ch][j / 2].x = a;
-        dAacc[ch][j / 2] = dhc[ch][j / 2] = make_float2(0.f, 0.f);
-      }
-    const int N4 = (p.N + 3) >> 2;
-    auto load_ckpt = [&](int c, float2 (&h)[2][2]) {
-#pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (c > 0 && d + ch < p.D && n0 < p.N)
-          v = __ldg(reinterpret_cast<const float4*>(p.ckpt) + (((int64_t)b * nck + c) * N4 + (n0 >> 2)) * p.D + d + ch);
-        h[ch][0] = make_float2(v.x, v.y), h[ch][1] = make_float2(v.z, v.w);
-      }
-    };
-    float2 hnext[2][2];
-    load_ckpt(nck - 1, hnext);
-    float4* const hst = hs + tid;  // + (tp * 2 + ch) * nscan_threads
-    float accB[2][4], accC[2][4];  // [state pair][mma accumulator]: 16 states x 8 timesteps per warp
-#pragma unroll
-    for (int i = 0; i < 2; ++i)
-#pragma unroll
-      for (int k = 0; k < 4; ++k) accB[i][k] = accC[i][k] = 0.f;
-    const bool st_writer = lane < 16;
-    const int st_off = sh * kCK * kBD + cl + ((lane & 4) ? 1 : 0);
-
-    int rslot = 0;
-    for (int it = 0; it < nck; ++it) {
-      const int c = nck - 1 - it;
-      const int ws = it & 1;
-      unsigned char* wbase = work_base + (size_t)ws * lay.work_bytes;
-      unsigned char* rbase = raw_base + (size_t)rslot * lay.raw_bytes;
-      const float2* wdl = reinterpret_cast<const float2*>(reinterpret_cast<const float*>(wbase + lay.w_dl) + cl);
-      const float2* wdu = reinterpret_cast<const float2*>(reinterpret_cast<const float*>(wbase + lay.w_du) + cl);
-      const float2* wdy = reinterpret_cast<const float2*>(reinterpret_cast<const float*>(wbase + lay.w_dy) + cl);
-      const float4* Bf = reinterpret_cast<const float4*>((sizeof(T) == 4 ? reinterpret_cast<const float*>(rbase + lay.raw_B)
-                                                                          : reinterpret_cast<const float*>(wbase + lay.w_Bf)) + n0);
-      const float4* Cf = reinterpret_cast<const float4*>((sizeof(T) == 4 ? reinterpret_cast<const float*>(rbase + lay.raw_C)
-                                                                          : reinterpret_cast<const float*>(wbase + lay.w_Cf)) + n0);
-      float* const stdst = reinterpret_cast<float*>(wbase + ((lane & 8) ? lay.w_pS : lay.w_pg)) + st_off;
-      float* const pbc = reinterpret_cast<float*>(wbase + lay.w_rB) + (cg * kCK + 2 * t4) * RS + n0;
-
-      float2 h[2][2];
-#pragma unroll
-      for (int ch = 0; ch < 2; ++ch) h[ch][0] = hnext[ch][0], h[ch][1] = hnext[ch][1];
-      bar_sync(1 + ws, bar_count);  // chunk c prepared
-
-      // ---- forward recompute: h_t of the EVEN steps of the chunk -> shared memory --------------------------
-#pragma unroll 4
-      for (int t = 0; t < kCK; ++t) {
-        const float2 dlv = wdl[t * (kBD / 2)], duv = wdu[t * (kBD / 2)];
-        const float4 b4 = Bf[t * (NPT / 4)];
-        const float2 Bp[2] = {make_float2(b4.x, b4.y), make_float2(b4.z, b4.w)};
-#pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
-          const float dl = ch ? dlv.y : dlv.x, du = ch ? duv.y : duv.x;
-          const float2 dl2 = make_float2(dl, dl), du2 = make_float2(du, du);
-#pragma unroll
-          for (int r = 0; r < 2; ++r) {
-            const float2 ga = __fmul2_rn(dl2, A2[ch][r]);
-            const float2 a = make_float2(ex2_approx(ga.x), ex2_approx(ga.y));
-            h[ch][r] = __ffma2_rn(a, h[ch][r], __fmul2_rn(du2, Bp[r]));
-          }
-          if ((t & 1) == 0)
-            hst[((t >> 1) * 2 + ch) * nscan_threads] = make_float4(h[ch][0].x, h[ch][0].y, h[ch][1].x, h[ch][1].y);
-        }
-      }
-      if (c > 0) load_ckpt(c - 1, hnext);
-
-      // ---- reverse sweep --------------------------------------------------------------------------------------
-      struct RevOps {
-        float2 dl, du, dy;
-        float4 B, C;
-      };
-      auto rev_load = [&](const int t, RevOps& o) {
-        o.dl = wdl[t * (kBD / 2)], o.du = wdu[t * (kBD / 2)], o.dy = wdy[t * (kBD / 2)];
-        o.B = Bf[t * (NPT / 4)], o.C = Cf[t * (NPT / 4)];
-      };
-      auto rev_compute = [&](const RevOps& o, const float2 (&hprev)[2][2], const bool odd, const uint32_t onehot) -> float {
-        const float2 Bp[2] = {make_float2(o.B.x, o.B.y), make_float2(o.B.z, o.B.w)};
-        const float2 Cp[2] = {make_float2(o.C.x, o.C.y), make_float2(o.C.z, o.C.w)};
-        float2 db[2][2], dc[2][2];
-        float v[4];  // gs(ch0), S(ch0), gs(ch1), S(ch1): sums over this thread's 4 states
-#pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
-          const float dl = ch ? o.dl.y : o.dl.x, du = ch ? o.du.y : o.du.x, dy = ch ? o.dy.y : o.dy.x;
-          const float2 dl2 = make_float2(dl, dl), du2 = make_float2(du, du), dy2 = make_float2(dy, dy);
-          const float2 ndu2 = make_float2(-du, -du);
-          float2 gs2 = make_float2(0.f, 0.f), S2 = make_float2(0.f, 0.f);
-#pragma unroll
-          for (int r = 0; r < 2; ++r) {
-            const float2 ga = __fmul2_rn(dl2, A2[ch][r]);
-            const float2 a = make_float2(ex2_approx(ga.x), ex2_approx(ga.y));
-            float2 hm, hc;  // hm = a_t * h_{t-1}, hc = h_t
-            if (odd) {
-              hm = __fmul2_rn(a, hprev[ch][r]);
-              hc = __ffma2_rn(du2, Bp[r], hm);
-            } else {
-              hc = hprev[ch][r];
-              hm = __ffma2_rn(ndu2, Bp[r], hc);
-            }
-            const float2 dh = __ffma2_rn(Cp[r], dy2, dhc[ch][r]);
-            dc[ch][r] = __fmul2_rn(dy2, hc);
-            db[ch][r] = __fmul2_rn(dh, du2);
-            const float2 gg = __fmul2_rn(dh, hm);  // dL/d(delta*A) for these two states
-            gs2 = __ffma2_rn(gg, A2[ch][r], gs2);
-            dAacc[ch][r] = __ffma2_rn(gg, dl2, dAacc[ch][r]);
-            S2 = __ffma2_rn(dh, Bp[r], S2);
-            dhc[ch][r] = __fmul2_rn(a, dh);
-          }
-          v[2 * ch] = gs2.x + gs2.y, v[2 * ch + 1] = S2.x + S2.y;
-        }
-        // sums over the octet's channels: tensor pipe, accumulated into the column of this timestep
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-          mma_colsum<sizeof(T) == 4>(accB[r], db[0][r], db[1][r], onehot);
-          mma_colsum<sizeof(T) == 4>(accC[r], dc[0][r], dc[1][r], onehot);
-        }
-        // sums over states: 4 values over the 8 g-lanes (lane bits 2..4)
-        reduce_scatter_step<4, 4>(v, lane & 4);
-        reduce_scatter_step<2, 8>(v, lane & 8);
-        reduce_scatter_step<1, 16>(v, lane & 16);
-        return v[0];  // lane bit 2: channel, lane bit 3: gs / S
-      };
-#pragma unroll 1
-      for (int tp = kCK / 2 - 1; tp >= 0; --tp) {
-        float2 he[2][2];
-#pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
-          const float4 h4 = hst[(tp * 2 + ch) * nscan_threads];
-          he[ch][0] = make_float2(h4.x, h4.y), he[ch][1] = make_float2(h4.z, h4.w);
-        }
-        RevOps o1, o0;
-        rev_load(2 * tp + 1, o1);
-        rev_load(2 * tp, o0);
-        const int col = (2 * tp) & 7;
-        const float r1 = rev_compute(o1, he, true, g == col + 1 ? 0x3f800000u : 0u);
-        const float r0 = rev_compute(o0, he, false, g == col ? 0x3f800000u : 0u);
-        if (st_writer) {
-          stdst[(2 * tp + 1) * kBD] = r1;
-          stdst[(2 * tp) * kBD] = r0;
-        }
-        if ((tp & 3) == 0) {
-          // flush 8 timesteps of dB | dC: this thread holds steps 2tp + 2*t4 (+1), states n0..n0+3
-          float* q = pbc + 2 * tp * RS;
-          *reinterpret_cast<float4*>(q) = make_float4(accB[0][0], accB[0][2], accB[1][0], accB[1][2]);
-          *reinterpret_cast<float4*>(q + RS) = make_float4(accB[0][1], accB[0][3], accB[1][1], accB[1][3]);
-          *reinterpret_cast<float4*>(q + NPT) = make_float4(accC[0][0], accC[0][2], accC[1][0], accC[1][2]);
-          *reinterpret_cast<float4*>(q + RS + NPT) = make_float4(accC[0][1], accC[0][3], accC[1][1], accC[1][3]);
-#pragma unroll
-          for (int i = 0; i < 2; ++i)
-#pragma unroll
-            for (int k = 0; k < 4; ++k) accB[i][k] = accC[i][k] = 0.f;
-        }
-      }
-      bar_arrive(3 + ws, bar_count);  // chunk c swept
-      rslot = (rslot + 1 == kBRing) ? 0 : rslot + 1;
-    }
-    // ---- epilogue: dA partial of this batch element -----------------------------------------------------------
-#pragma unroll
-    for (int ch = 0; ch < 2; ++ch)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int n = n0 + j;
-        if (d + ch < p.D && n < p.N)
-          p.ws_dA[((int64_t)b * p.N + n) * p.D + d + ch] = (j & 1) ? dAacc[ch][j / 2].y : dAacc[ch][j / 2].x;
-      }
-    return;
-   }
-  } else
   if (warp < NW) {
     // ========================================= SCAN WARPS ===============================================
     // lane <-> channel (32 channels), this warp's slice of NPER states in registers, packed in pairs along n.
@@ -661,8 +375,7 @@ __global__ void __launch_bounds__((NW + kBHelperWarps) * 32, 1) scan_bwd_kernel(
       const float* pg = reinterpret_cast<const float*>(wbase + lay.w_pg) + o;
       const float* pS = reinterpret_cast<const float*>(wbase + lay.w_pS) + o;
       float2 g01 = make_float2(0.f, 0.f), g23 = g01, S01 = g01, S23 = g01;
-#pragma unroll
-      for (int w = 0; w < NPART; ++w) {
+      for (int w = 0; w < NW; ++w) {
         const float4 a = *reinterpret_cast<const float4*>(pg + w * kCK * kBD);
         const float4 s4 = *reinterpret_cast<const float4*>(pS + w * kCK * kBD);
         g01 = __fadd2_rn(g01, make_float2(a.x, a.y)), g23 = __fadd2_rn(g23, make_float2(a.z, a.w));
@@ -709,24 +422,7 @@ __global__ void __launch_bounds__((NW + kBHelperWarps) * 32, 1) scan_bwd_kernel(
       float* wsC = p.ws_dC + (((int64_t)b * p.ntiles + tile) * p.L + t0) * p.N;
       const float* redB = reinterpret_cast<const float*>(wbase + lay.w_rB);
       const float* redC = reinterpret_cast<const float*>(wbase + lay.w_rC);
-      if constexpr (kMma) {
-        // sum the four channel-octet partials (fixed order); NPT == N here
-        constexpr int Q = NPT / 4;
-        for (int i = ht; i < rv * Q; i += kBHelperThreads) {
-          const int t = i / Q, q = i - t * Q;
-          const float* src = redB + t * RS + 4 * q;
-          float4 sB = *reinterpret_cast<const float4*>(src), sC = *reinterpret_cast<const float4*>(src + NPT);
-#pragma unroll
-          for (int o = 1; o < 4; ++o) {
-            const float4 xb = *reinterpret_cast<const float4*>(src + o * kCK * RS);
-            const float4 xc = *reinterpret_cast<const float4*>(src + o * kCK * RS + NPT);
-            sB.x += xb.x, sB.y += xb.y, sB.z += xb.z, sB.w += xb.w;
-            sC.x += xc.x, sC.y += xc.y, sC.z += xc.z, sC.w += xc.w;
-          }
-          reinterpret_cast<float4*>(wsB)[i] = sB;
-          reinterpret_cast<float4*>(wsC)[i] = sC;
-        }
-      } else if (NPT == p.N && (p.N & 3) == 0) {
+      if (NPT == p.N && (p.N & 3) == 0) {
         const int nv = rv * p.N / 4;
         for (int i = ht; i < nv; i += kBHelperThreads) {
           reinterpret_cast<float4*>(wsB)[i] = reinterpret_cast<const float4*>(redB)[i];
@@ -839,8 +535,8 @@ __global__ void scan_bwd_finalize_kernel(const ScanBwdParams p, int rows_per_blo
 }
 
 template <typename T, int kCK>
-static size_t bwd_smem_bytes(int NW, int NPT, int NPER, bool mma) {
-  const BwdLayout<T, kCK> lay(NW, NPT, NPER, mma);
+static size_t bwd_smem_bytes(int NW, int NPT, int NPER) {
+  const BwdLayout<T, kCK> lay(NW, NPT, NPER);
   return (size_t)kBRing * lay.raw_bytes + (size_t)2 * lay.work_bytes + lay.hs_bytes;
 }
 
@@ -858,12 +554,15 @@ static size_t bwd_workspace_layout(int B, int L, int D, int N, size_t* o_dB, siz
   return off;
 }
 
-template <typename T, int NPER, int NW, int kCK, bool kMma = false>
+template <typename T>
+static int launch_finalize(const ScanBwdParams& p, cudaStream_t stream);
+
+template <typename T, int NPER, int NW, int kCK>
 static int launch_bwd(const ScanBwdParams& p, cudaStream_t stream) {
-  const size_t smem = bwd_smem_bytes<T, kCK>(NW, p.NPT, NPER, kMma);
+  const size_t smem = bwd_smem_bytes<T, kCK>(NW, p.NPT, NPER);
   if (smem > 227 * 1024)
     return set_error(MAMBA_ESIZE, "scan_bwd: d_state %d needs %zu B of shared memory", p.N, smem);
-  auto kern = scan_bwd_kernel<T, NPER, NW, kCK, kMma>;
+  auto kern = scan_bwd_kernel<T, NPER, NW, kCK>;
   static thread_local size_t configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -875,6 +574,11 @@ static int launch_bwd(const ScanBwdParams& p, cudaStream_t stream) {
   count_launch();
   int rc = check_launch("scan_bwd");
   if (rc) return rc;
+  return launch_finalize<T>(p, stream);
+}
+
+template <typename T>
+static int launch_finalize(const ScanBwdParams& p, cudaStream_t stream) {
   const int rows_per_block = 8;
   const int nrow_blocks = (int)(((int64_t)p.B * p.L + rows_per_block - 1) / rows_per_block);
   const int nsmall = ceil_div(p.D * p.N, 256 * 4);
@@ -899,19 +603,15 @@ static int bwd_dispatch_ck(const ScanBwdParams& p, cudaStream_t stream) {
   return p.ck == 8 ? bwd_dispatch_nw<T, NPER, 8>(p, stream) : bwd_dispatch_nw<T, NPER, 16>(p, stream);
 }
 
-// Tensor-pipe variant: d_state 32 or 64 exactly (4 or 8 scan warps of 8 channels x 32 states).
-template <typename T>
-static int bwd_dispatch_mma(ScanBwdParams& p, cudaStream_t stream) {
-  p.NW = p.N / 8;
-  p.NPT = p.N;
-  if (p.N == 64) return p.ck == 8 ? launch_bwd<T, 8, 8, 8, true>(p, stream) : launch_bwd<T, 8, 8, 16, true>(p, stream);
-  if (p.N == 32) return p.ck == 8 ? launch_bwd<T, 8, 4, 8, true>(p, stream) : launch_bwd<T, 8, 4, 16, true>(p, stream);
-  return set_error(MAMBA_EINVAL, "scan_bwd: variant 1 (tensor-pipe reductions) needs d_state 32 or 64 (got %d)", p.N);
-}
-
 template <typename T>
 static int bwd_dispatch(ScanBwdParams& p, int nper, cudaStream_t stream) {
-  if (nper == 1) return bwd_dispatch_mma<T>(p, stream);
+  if (nper == 1) {  // fused recompute/reverse kernel with tensor-pipe channel sums (scan_bwd_fused.cu)
+    if (p.N != 64 && p.N != 32)
+      return set_error(MAMBA_EINVAL, "scan_bwd: variant 1 (fused, tensor-pipe reductions) needs d_state 32 or 64 (got %d)", p.N);
+    p.NW = p.N / 8, p.NPT = p.N;
+    const int rc = launch_scan_bwd_fused<T>(p, stream);
+    return rc ? rc : launch_finalize<T>(p, stream);
+  }
   p.NW = ceil_div(p.N, nper);
   if (p.NW > kBMaxWarps) return set_error(MAMBA_ESIZE, "scan_bwd: d_state %d too large (max %d)", p.N, kBMaxWarps * 16);
   p.NW = p.NW <= 2 ? p.NW : (p.NW <= 4 ? 4 : 8);  // instantiated warp counts
@@ -995,10 +695,12 @@ extern "C" int mamba_scan_bwd(const MambaScanBwdArgs* a, void* stream) {
   p.vec_dz = a->dz ? bvec_ok(a->dz, a->dz_bs, a->dz_ls, elt) : 0;
   p.vec_ck = a->ckpt && aligned16(a->ckpt) && (p.D % 4 == 0);
 
-  // variant: 0 = auto, 1 = tensor-pipe channel reductions (d_state 32 / 64), 4 / 8 / 16 = lane<->channel kernel
-  // with that many states per thread
+  // variant: 0 = auto, 1 = fused kernel with tensor-pipe channel reductions (d_state 32 / 64), 4 / 8 / 16 =
+  // lane<->channel kernel with that many states per thread
   int nper = a->variant;
-  if (nper == 0) nper = (p.N == 64 || p.N == 32) ? 1 : (p.N <= 32 ? 4 : 8);
+  // auto: the fused kernel wins with bf16 I/O (plain tf32 column sums); with fp32 I/O its split-tf32 MMAs cost
+  // more than the shuffles they replace
+  if (nper == 0) nper = ((p.N == 64 || p.N == 32) && a->dtype == MAMBA_BF16) ? 1 : (p.N <= 32 ? 4 : 8);
   while (nper > 1 && nper < 16 && ceil_div(p.N, nper) > kBMaxWarps) nper *= 2;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   return a->dtype == MAMBA_F32 ? bwd_dispatch<float>(p, nper, st) : bwd_dispatch<__nv_bfloat16>(p, nper, st);
