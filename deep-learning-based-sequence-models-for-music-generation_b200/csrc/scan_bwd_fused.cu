@@ -30,41 +30,58 @@ constexpr int kFIn = 3;   // operand ring depth (chunk it is read by the reverse
 constexpr int kFRaw = 2;  // cp.async ring depth
 constexpr int kFOut = 2;  // result ring depth
 
-template <typename T, int kCK>
+constexpr int align128(int x) { return (x + 127) & ~127; }
+
+// Shared-memory map (all offsets compile-time constants so that every shared access is base register + immediate).
+template <typename T, int NW, int kCK>
 struct FusedLayout {
-  int raw_u, raw_dl, raw_z, raw_do, raw_B, raw_C, raw_bytes;
-  int w_dl, w_du, w_dy, w_Bf, w_Cf, in_bytes;
-  int o_pg, o_pS, o_bc, out_bytes;
-  int off_raw, off_in, off_out, off_hs, total;
-  __host__ __device__ FusedLayout(int NW, int NPT) {
-    int o = 0;
-    raw_u = o, o += kCK * kBD * (int)sizeof(T);
-    raw_dl = o, o += kCK * kBD * (int)sizeof(T);
-    raw_z = o, o += kCK * kBD * (int)sizeof(T);
-    raw_do = o, o += kCK * kBD * (int)sizeof(T);
-    raw_B = o, o += kCK * NPT * (int)sizeof(T);
-    raw_C = o, o += kCK * NPT * (int)sizeof(T);
-    raw_bytes = (o + 127) & ~127;
-    o = 0;
-    w_dl = o, o += kCK * kBD * 4;
-    w_du = o, o += kCK * kBD * 4;
-    w_dy = o, o += kCK * kBD * 4;
-    w_Bf = o, o += kCK * NPT * 4;
-    w_Cf = o, o += kCK * NPT * 4;
-    in_bytes = (o + 127) & ~127;
-    const int nsh = NW >= 4 ? NW / 4 : 1;
-    o = 0;
-    o_pg = o, o += nsh * kCK * kBD * 4;
-    o_pS = o, o += nsh * kCK * kBD * 4;
-    o_bc = o, o += 4 * kCK * (2 * NPT + 4) * 4;  // [channel octet][step][dB | dC | pad]: row stride == 4 mod 16 floats
-    out_bytes = (o + 127) & ~127;
-    off_raw = 0;
-    off_in = off_raw + kFRaw * raw_bytes;
-    off_out = off_in + kFIn * in_bytes;
-    off_hs = off_out + kFOut * out_bytes;
-    total = off_hs + (kCK / 2) * 2 * NW * 32 * 16;  // float4 [CK/2][2 channels][scan threads]
-  }
+  static constexpr int S = (int)sizeof(T);
+  static constexpr int NPT = NW * 8;                 // d_state
+  static constexpr int RS = 2 * NPT + 4;             // row stride (floats) of the dB|dC octet partials: == 4 mod 16
+  static constexpr int NSH = NW >= 4 ? NW / 4 : 1;   // state halves
+  // raw slot (cp.async targets, element type T)
+  static constexpr int raw_u = 0;
+  static constexpr int raw_dl = raw_u + kCK * kBD * S;
+  static constexpr int raw_z = raw_dl + kCK * kBD * S;
+  static constexpr int raw_do = raw_z + kCK * kBD * S;
+  static constexpr int raw_B = raw_do + kCK * kBD * S;
+  static constexpr int raw_C = raw_B + kCK * NPT * S;
+  static constexpr int raw_bytes = align128(raw_C + kCK * NPT * S);
+  // operand slot (fp32)
+  static constexpr int w_dl = 0;
+  static constexpr int w_du = w_dl + kCK * kBD * 4;
+  static constexpr int w_dy = w_du + kCK * kBD * 4;
+  static constexpr int w_Bf = w_dy + kCK * kBD * 4;
+  static constexpr int w_Cf = w_Bf + kCK * NPT * 4;
+  static constexpr int in_bytes = align128(w_Cf + kCK * NPT * 4);
+  // result slot (fp32)
+  static constexpr int o_pg = 0;
+  static constexpr int o_pS = o_pg + NSH * kCK * kBD * 4;
+  static constexpr int o_bc = o_pS + NSH * kCK * kBD * 4;  // [channel octet][step][dB | dC | pad]
+  static constexpr int out_bytes = align128(o_bc + 4 * kCK * RS * 4);
+  static constexpr int off_raw = 0;
+  static constexpr int off_in = off_raw + kFRaw * raw_bytes;
+  static constexpr int off_out = off_in + kFIn * in_bytes;
+  static constexpr int off_hs = off_out + kFOut * out_bytes;
+  static constexpr int hs_slot = 2 * NW * 32 * 16;          // one even step: float4 [2 channels][scan threads]
+  static constexpr int total = off_hs + (kCK / 2) * hs_slot;
 };
+
+// shared-memory accesses by 32-bit shared address (no generic->shared conversion inside the loops)
+__device__ __forceinline__ float2 lds64(uint32_t a) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v)); }
+__device__ __forceinline__ void sts128(uint32_t a, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
+}
 
 // 4 consecutive channels of one (b, t) row from global memory (post-pass operands; L2 hits)
 template <typename T>
@@ -90,9 +107,9 @@ template <typename T, int NW, int kCK>
 __global__ void __launch_bounds__((NW + kBHelperWarps) * 32, 1) scan_bwd_fused_kernel(const ScanBwdParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  constexpr int NPT = NW * 8;       // d_state (32 or 64)
-  constexpr int RS = 2 * NPT + 4;   // row stride of the dB|dC octet partials
-  constexpr int NSH = NW >= 4 ? NW / 4 : 1;
+  using Lay = FusedLayout<T, NW, kCK>;
+  constexpr Lay lay{};
+  constexpr int NPT = Lay::NPT, RS = Lay::RS, NSH = Lay::NSH;
   constexpr int K = kCK / 2;        // (odd, even) step pairs per chunk
   constexpr int nscan_threads = NW * 32;
   constexpr int bar_count = nscan_threads + kBHelperThreads;
@@ -100,11 +117,9 @@ __global__ void __launch_bounds__((NW + kBHelperWarps) * 32, 1) scan_bwd_fused_k
   const int b = blockIdx.y, tile = blockIdx.x;
   const int d0 = tile * kBD;
   const int dvalid = min(kBD, p.D - d0);
-  const FusedLayout<T, kCK> lay(NW, NPT);
-  unsigned char* const raw_base = smem + lay.off_raw;
-  unsigned char* const in_base = smem + lay.off_in;
-  unsigned char* const out_base = smem + lay.off_out;
-  float4* const hs = reinterpret_cast<float4*>(smem + lay.off_hs);
+  unsigned char* const raw_base = smem + Lay::off_raw;
+  unsigned char* const in_base = smem + Lay::off_in;
+  unsigned char* const out_base = smem + Lay::off_out;
   const int nck = p.nck;
   const bool has_z = p.flags & MAMBA_FLAG_HAS_Z;
   // named barriers: 1..3 = READY[operand slot], 4..5 = DONE[result slot], 6 = helpers only.
@@ -138,43 +153,31 @@ __global__ void __launch_bounds__((NW + kBHelperWarps) * 32, 1) scan_bwd_fused_k
         h[ch][0] = make_float2(v.x, v.y), h[ch][1] = make_float2(v.z, v.w);
       }
     };
-    float4* const hst = hs + tid;  // + (slot * 2 + ch) * nscan_threads
     float accB[2][4], accC[2][4];  // [state pair][mma accumulator]: 16 states x 8 timesteps per warp
 #pragma unroll
     for (int i = 0; i < 2; ++i)
 #pragma unroll
       for (int k = 0; k < 4; ++k) accB[i][k] = accC[i][k] = 0.f;
     const bool st_writer = lane < 16;
-    const int st_off = sh * kCK * kBD + cl + ((lane & 4) ? 1 : 0);
 
-    struct InPtrs {
-      const float2 *dl, *du, *dy;
-      const float4 *B, *C;
-    };
-    auto in_ptrs = [&](int slot) {
-      unsigned char* w = in_base + (size_t)slot * lay.in_bytes;
-      InPtrs q;
-      q.dl = reinterpret_cast<const float2*>(reinterpret_cast<const float*>(w + lay.w_dl) + cl);
-      q.du = reinterpret_cast<const float2*>(reinterpret_cast<const float*>(w + lay.w_du) + cl);
-      q.dy = reinterpret_cast<const float2*>(reinterpret_cast<const float*>(w + lay.w_dy) + cl);
-      q.B = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(w + lay.w_Bf) + n0);
-      q.C = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(w + lay.w_Cf) + n0);
-      return q;
-    };
+    // 32-bit shared addresses of this thread's operands (row strides: 128 B per step for the per-channel arrays,
+    // NPT*4 B per step for B / C); every access below is one of these registers + an immediate
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
+    const uint32_t in0 = sbase + Lay::off_in + cl * 4;           // + slot*in_bytes + {w_dl,w_du,w_dy} + t*128
+    const uint32_t bc0 = sbase + Lay::off_in + Lay::w_Bf + n0 * 4;  // + slot*in_bytes + {0, w_Cf-w_Bf} + t*NPT*4
+    const uint32_t hs0 = sbase + Lay::off_hs + tid * 16;         // + slot*hs_slot + ch*nscan_threads*16
+    const uint32_t st0 = sbase + Lay::off_out + ((lane & 8) ? Lay::o_pS : Lay::o_pg) +
+                         (sh * kCK * kBD + cl + ((lane & 4) ? 1 : 0)) * 4;          // + oslot*out_bytes + t*128
+    const uint32_t pb0 = sbase + Lay::off_out + Lay::o_bc + ((cg * kCK + 2 * t4) * RS + n0) * 4;  // + oslot*.. + t*RS*4
+    constexpr int kRowC = kBD * 4, kRowS = NPT * 4, kCoff = Lay::w_Cf - Lay::w_Bf;
+    constexpr int kHch = nscan_threads * 16;
 
     // one recompute step: h <- exp2(delta*A) * h + delta*u*B
-    struct RecOps {
-      float2 dl, du;
-      float4 B;
-    };
-    auto rec_load = [&](const InPtrs& q, int t, RecOps& o) {
-      o.dl = q.dl[t * (kBD / 2)], o.du = q.du[t * (kBD / 2)], o.B = q.B[t * (NPT / 4)];
-    };
-    auto rec_step = [&](const RecOps& o, float2 (&h)[2][2]) {
-      const float2 Bp[2] = {make_float2(o.B.x, o.B.y), make_float2(o.B.z, o.B.w)};
+    auto rec_step = [&](const float2 dlv, const float2 duv, const float4 B4, float2 (&h)[2][2]) {
+      const float2 Bp[2] = {make_float2(B4.x, B4.y), make_float2(B4.z, B4.w)};
 #pragma unroll
       for (int ch = 0; ch < 2; ++ch) {
-        const float dl = ch ? o.dl.y : o.dl.x, du = ch ? o.du.y : o.du.x;
+        const float dl = ch ? dlv.y : dlv.x, du = ch ? duv.y : duv.x;
         const float2 dl2 = make_float2(dl, dl), du2 = make_float2(du, du);
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
@@ -184,29 +187,22 @@ __global__ void __launch_bounds__((NW + kBHelperWarps) * 32, 1) scan_bwd_fused_k
         }
       }
     };
-    auto hs_store = [&](int slot, const float2 (&h)[2][2]) {
-#pragma unroll
-      for (int ch = 0; ch < 2; ++ch)
-        hst[(slot * 2 + ch) * nscan_threads] = make_float4(h[ch][0].x, h[ch][0].y, h[ch][1].x, h[ch][1].y);
+    auto hs_store = [&](uint32_t a, const float2 (&h)[2][2]) {
+      sts128(a, make_float4(h[0][0].x, h[0][0].y, h[0][1].x, h[0][1].y));
+      sts128(a + kHch, make_float4(h[1][0].x, h[1][0].y, h[1][1].x, h[1][1].y));
     };
 
-    // one reverse step
-    struct RevOps {
-      float2 dl, du, dy;
-      float4 B, C;
-    };
-    auto rev_load = [&](const InPtrs& q, int t, RevOps& o) {
-      o.dl = q.dl[t * (kBD / 2)], o.du = q.du[t * (kBD / 2)], o.dy = q.dy[t * (kBD / 2)];
-      o.B = q.B[t * (NPT / 4)], o.C = q.C[t * (NPT / 4)];
-    };
-    auto rev_compute = [&](const RevOps& o, const float2 (&hprev)[2][2], const bool odd, const bool onehot) -> float {
-      const float2 Bp[2] = {make_float2(o.B.x, o.B.y), make_float2(o.B.z, o.B.w)};
-      const float2 Cp[2] = {make_float2(o.C.x, o.C.y), make_float2(o.C.z, o.C.w)};
+    // one reverse step; returns this lane's state-sum value BEFORE the last butterfly stage (lane ^ 16), which the
+    // caller finishes one loop iteration later so that the shuffle latency is off the critical path
+    auto rev_compute = [&](const float2 dlv, const float2 duv, const float2 dyv, const float4 B4, const float4 C4,
+                           const float2 (&hprev)[2][2], const bool odd, const bool onehot) -> float {
+      const float2 Bp[2] = {make_float2(B4.x, B4.y), make_float2(B4.z, B4.w)};
+      const float2 Cp[2] = {make_float2(C4.x, C4.y), make_float2(C4.z, C4.w)};
       float2 xb[2][2], xc[2][2];  // A-fragments of the dB / dC column sums
       float v[4];                 // gs(ch0), S(ch0), gs(ch1), S(ch1): sums over this thread's 4 states
 #pragma unroll
       for (int ch = 0; ch < 2; ++ch) {
-        const float dl = ch ? o.dl.y : o.dl.x, du = ch ? o.du.y : o.du.x, dy = ch ? o.dy.y : o.dy.x;
+        const float dl = ch ? dlv.y : dlv.x, du = ch ? duv.y : duv.x, dy = ch ? dyv.y : dyv.x;
         const float2 dl2 = make_float2(dl, dl), du2 = make_float2(du, du), dy2 = make_float2(dy, dy);
         const float2 ndu2 = make_float2(-du, -du);
         float2 gs2 = make_float2(0.f, 0.f), S2 = make_float2(0.f, 0.f);
@@ -254,8 +250,8 @@ __global__ void __launch_bounds__((NW + kBHelperWarps) * 32, 1) scan_bwd_fused_k
           }
         }
       } else {
-        const uint32_t bu0 = onehot ? __float_as_uint(o.du.x) : 0u, bu1 = onehot ? __float_as_uint(o.du.y) : 0u;
-        const uint32_t by0 = onehot ? __float_as_uint(o.dy.x) : 0u, by1 = onehot ? __float_as_uint(o.dy.y) : 0u;
+        const uint32_t bu0 = onehot ? __float_as_uint(duv.x) : 0u, bu1 = onehot ? __float_as_uint(duv.y) : 0u;
+        const uint32_t by0 = onehot ? __float_as_uint(dyv.x) : 0u, by1 = onehot ? __float_as_uint(dyv.y) : 0u;
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
           mma_tf32(accB[r], __float_as_uint(xb[0][r].x), __float_as_uint(xb[0][r].y), __float_as_uint(xb[1][r].x),
@@ -264,10 +260,9 @@ __global__ void __launch_bounds__((NW + kBHelperWarps) * 32, 1) scan_bwd_fused_k
                    __float_as_uint(xc[1][r].y), by0, by1);
         }
       }
-      // sums over states: 4 values over the 8 g-lanes (lane bits 2..4)
+      // sums over states: 4 values over the 8 g-lanes (lane bits 2..4); the last stage is the caller's
       reduce_scatter_step<4, 4>(v, lane & 4);
       reduce_scatter_step<2, 8>(v, lane & 8);
-      reduce_scatter_step<1, 16>(v, lane & 16);
       return v[0];  // lane bit 2: channel, lane bit 3: gs / S
     };
 
@@ -276,71 +271,96 @@ __global__ void __launch_bounds__((NW + kBHelperWarps) * 32, 1) scan_bwd_fused_k
     load_ckpt(nck - 1, hR);
     load_ckpt(nck - 2, hnext);  // start state of iteration 1's chunk (zero when nck == 1 or for chunk 0)
     bar_sync(1, bar_count);
-    {
-      const InPtrs q = in_ptrs(0);
 #pragma unroll 2
-      for (int i = 0; i < K; ++i) {
-        RecOps e, o;
-        rec_load(q, 2 * i, e), rec_load(q, 2 * i + 1, o);
-        rec_step(e, hR);
-        hs_store(i, hR);  // iteration 0: even step 2i -> slot i
-        rec_step(o, hR);
-      }
+    for (int i = 0; i < K; ++i) {
+      const uint32_t a = in0 + 2 * i * kRowC, bq = bc0 + 2 * i * kRowS;
+      const float2 dle = lds64(a + Lay::w_dl), due = lds64(a + Lay::w_du);
+      const float2 dlo = lds64(a + Lay::w_dl + kRowC), duo = lds64(a + Lay::w_du + kRowC);
+      const float4 Be = lds128(bq), Bo = lds128(bq + kRowS);
+      rec_step(dle, due, Be, hR);
+      hs_store(hs0 + i * Lay::hs_slot, hR);  // iteration 0: even step 2i -> slot i
+      rec_step(dlo, duo, Bo, hR);
     }
 
-    int vslot = 0;  // operand slot of iteration `it`
+    int vslot = 0;                 // operand slot of iteration `it`
+    float pend1 = 0.f, pend0 = 0.f;  // state sums of the previous step pair, one butterfly stage short
+    uint32_t pend_addr = 0;          // where they go (0: nothing pending)
+    auto finish_pending = [&]() {
+      const float f1 = pend1 + __shfl_xor_sync(0xffffffffu, pend1, 16);
+      const float f0 = pend0 + __shfl_xor_sync(0xffffffffu, pend0, 16);
+      if (st_writer && pend_addr) {
+        sts32(pend_addr + kRowC, f1);
+        sts32(pend_addr, f0);
+      }
+    };
     for (int it = 0; it < nck; ++it) {
       const int rslot = vslot + 1 == kFIn ? 0 : vslot + 1;
       const bool has_next = it + 1 < nck;
-      const bool par = it & 1;  // even step j of this chunk lives in slot (par ? K-1-j : j)
-      unsigned char* obase = out_base + (size_t)(it & 1) * lay.out_bytes;
-      float* const stdst = reinterpret_cast<float*>(obase + ((lane & 8) ? lay.o_pS : lay.o_pg)) + st_off;
-      float* const pbc = reinterpret_cast<float*>(obase + lay.o_bc) + (cg * kCK + 2 * t4) * RS + n0;
-      const InPtrs qv = in_ptrs(vslot), qr = in_ptrs(rslot);
+      const bool par = it & 1;  // even step j of this chunk lives in hs slot (par ? K-1-j : j)
+      const uint32_t oslot = (it & 1) * Lay::out_bytes;
 #pragma unroll
       for (int ch = 0; ch < 2; ++ch) hR[ch][0] = hnext[ch][0], hR[ch][1] = hnext[ch][1];
       // operands of the next chunk are prepared — and (also on the last iteration, where the helpers arrive without
       // a pre-pass) the post-pass that read this iteration's result slot two chunks ago is over
       bar_sync(1 + rslot, bar_count);
       if (has_next) load_ckpt(nck - 3 - it, hnext);  // its latency hides behind this whole iteration
+      // running addresses: reverse sweep walks down from step pair K-1, recompute walks up from step pair 0
+      uint32_t va = in0 + vslot * Lay::in_bytes + (kCK - 2) * kRowC;   // step 2tp of the swept chunk
+      uint32_t vb = bc0 + vslot * Lay::in_bytes + (kCK - 2) * kRowS;
+      uint32_t ra = in0 + rslot * Lay::in_bytes;                       // step 2i of the recomputed chunk
+      uint32_t rb = bc0 + rslot * Lay::in_bytes;
+      uint32_t ha = hs0 + (par ? 0 : (K - 1) * Lay::hs_slot);          // hs slot read (and then rewritten)
+      const int hstep = par ? Lay::hs_slot : -Lay::hs_slot;
+      uint32_t sa = st0 + oslot + (kCK - 2) * kRowC;                   // state sums of step 2tp
+      uint32_t pa = pb0 + oslot + (kCK - 2) * RS * 4;                  // dB|dC flush base of step 2tp (tp & 3 == 0)
+      // delta of the first iteration's four steps (the MUFU inputs), prefetched one iteration ahead from here on
+      float2 dl1 = lds64(va + Lay::w_dl + kRowC), dl0 = lds64(va + Lay::w_dl);
+      float2 dle = lds64(ra + Lay::w_dl), dlo = lds64(ra + Lay::w_dl + kRowC);
+
       auto body = [&](const int i, auto with_rec) {
         constexpr bool kRec = decltype(with_rec)::value;
         const int tp = K - 1 - i;
-        const int slot = par ? i : tp;
-        float2 he[2][2];
-#pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
-          const float4 h4 = hst[(slot * 2 + ch) * nscan_threads];
-          he[ch][0] = make_float2(h4.x, h4.y), he[ch][1] = make_float2(h4.z, h4.w);
-        }
-        RevOps o1, o0;
-        rev_load(qv, 2 * tp + 1, o1);
-        rev_load(qv, 2 * tp, o0);
-        RecOps e, o;
-        if constexpr (kRec) rec_load(qr, 2 * i, e), rec_load(qr, 2 * i + 1, o);
-        const int col = (2 * tp) & 7;
-        if constexpr (kRec) rec_step(e, hR);
-        const float r1 = rev_compute(o1, he, true, g == col + 1);
+        // loads of this iteration
+        const float4 he0 = lds128(ha), he1 = lds128(ha + kHch);
+        const float2 du1 = lds64(va + Lay::w_du + kRowC), dy1 = lds64(va + Lay::w_dy + kRowC);
+        const float4 B1 = lds128(vb + kRowS), C1 = lds128(vb + kCoff + kRowS);
+        const float2 du0 = lds64(va + Lay::w_du), dy0 = lds64(va + Lay::w_dy);
+        const float4 B0 = lds128(vb), C0 = lds128(vb + kCoff);
+        float2 due, duo;
+        float4 Be, Bo;
         if constexpr (kRec) {
-          hs_store(slot, hR);  // the slot just read: next chunk's even step 2i
-          rec_step(o, hR);
+          due = lds64(ra + Lay::w_du), duo = lds64(ra + Lay::w_du + kRowC);
+          Be = lds128(rb), Bo = lds128(rb + kRowS);
         }
-        const float r0 = rev_compute(o0, he, false, g == col);
-        if (st_writer) {
-          stdst[(2 * tp + 1) * kBD] = r1;
-          stdst[(2 * tp) * kBD] = r0;
+        finish_pending();  // last butterfly stage + store of the previous pair's state sums
+        const float2 he[2][2] = {{make_float2(he0.x, he0.y), make_float2(he0.z, he0.w)},
+                                 {make_float2(he1.x, he1.y), make_float2(he1.z, he1.w)}};
+        const int col = (2 * tp) & 7;
+        if constexpr (kRec) rec_step(dle, due, Be, hR);
+        pend1 = rev_compute(dl1, du1, dy1, B1, C1, he, true, g == col + 1);
+        if constexpr (kRec) {
+          hs_store(ha, hR);  // the slot just read: next chunk's even step 2i
+          rec_step(dlo, duo, Bo, hR);
         }
+        pend0 = rev_compute(dl0, du0, dy0, B0, C0, he, false, g == col);
+        pend_addr = sa;
         if ((tp & 3) == 0) {
           // flush 8 timesteps of dB | dC: this thread holds steps 2tp + 2*t4 (+1), states n0..n0+3
-          float* q = pbc + 2 * tp * RS;
-          *reinterpret_cast<float4*>(q) = make_float4(accB[0][0], accB[0][2], accB[1][0], accB[1][2]);
-          *reinterpret_cast<float4*>(q + RS) = make_float4(accB[0][1], accB[0][3], accB[1][1], accB[1][3]);
-          *reinterpret_cast<float4*>(q + NPT) = make_float4(accC[0][0], accC[0][2], accC[1][0], accC[1][2]);
-          *reinterpret_cast<float4*>(q + RS + NPT) = make_float4(accC[0][1], accC[0][3], accC[1][1], accC[1][3]);
+          sts128(pa, make_float4(accB[0][0], accB[0][2], accB[1][0], accB[1][2]));
+          sts128(pa + RS * 4, make_float4(accB[0][1], accB[0][3], accB[1][1], accB[1][3]));
+          sts128(pa + NPT * 4, make_float4(accC[0][0], accC[0][2], accC[1][0], accC[1][2]));
+          sts128(pa + (RS + NPT) * 4, make_float4(accC[0][1], accC[0][3], accC[1][1], accC[1][3]));
 #pragma unroll
           for (int w = 0; w < 2; ++w)
 #pragma unroll
             for (int k = 0; k < 4; ++k) accB[w][k] = accC[w][k] = 0.f;
+        }
+        // advance; prefetch the next iteration's delta (past the chunk on the last iteration: in-bounds, unused)
+        va -= 2 * kRowC, vb -= 2 * kRowS, sa -= 2 * kRowC, pa -= 2 * RS * 4, ha += hstep;
+        dl1 = lds64(va + Lay::w_dl + kRowC), dl0 = lds64(va + Lay::w_dl);
+        if constexpr (kRec) {
+          ra += 2 * kRowC, rb += 2 * kRowS;
+          dle = lds64(ra + Lay::w_dl), dlo = lds64(ra + Lay::w_dl + kRowC);
         }
       };
       if (has_next) {
@@ -350,7 +370,9 @@ __global__ void __launch_bounds__((NW + kBHelperWarps) * 32, 1) scan_bwd_fused_k
 #pragma unroll 1
         for (int i = 0; i < K; ++i) body(i, std::false_type{});
       }
-      bar_arrive(4 + (it & 1), bar_count);  // chunk swept: results of this iteration are complete
+      finish_pending();  // the results of this iteration must be complete before DONE
+      pend_addr = 0;
+      bar_arrive(4 + (it & 1), bar_count);  // chunk swept
       vslot = rslot;
     }
     // ---- epilogue: dA partial of this batch element -----------------------------------------------------------
@@ -593,8 +615,7 @@ __global__ void __launch_bounds__((NW + kBHelperWarps) * 32, 1) scan_bwd_fused_k
 
 template <typename T, int NW, int kCK>
 static int launch_fused(const ScanBwdParams& p, cudaStream_t stream) {
-  const FusedLayout<T, kCK> lay(NW, NW * 8);
-  const size_t smem = (size_t)lay.total;
+  const size_t smem = (size_t)FusedLayout<T, NW, kCK>::total;
   if (smem > 227 * 1024) return set_error(MAMBA_ESIZE, "scan_bwd (fused): needs %zu B of shared memory", smem);
   auto kern = scan_bwd_fused_kernel<T, NW, kCK>;
   static thread_local bool configured = false;
