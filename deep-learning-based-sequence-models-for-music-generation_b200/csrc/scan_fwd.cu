@@ -57,7 +57,7 @@ __device__ __forceinline__ float4 ld4_as_f32(const __nv_bfloat16* p) {
 template <typename T>
 struct FwdLayout {
   int raw_u, raw_dl, raw_z, raw_B, raw_C, raw_bytes;
-  int w_dlu, w_y, work_bytes;
+  int w_dlu, w_y, w_Bf, w_Cf, work_bytes;
   __host__ __device__ FwdLayout(int NS, int NPT) {
     int o = 0;
     raw_u = o, o += kTS * kDT * (int)sizeof(T);
@@ -69,6 +69,8 @@ struct FwdLayout {
     o = 0;
     w_dlu = o, o += kTS * kDT * 8;
     w_y = o, o += NS * kTS * kDT * 4;
+    w_Bf = o, o += (sizeof(T) == 4 ? 0 : kTS * NPT * 4);  // bf16 I/O: B / C widened by the helpers' pre-pass
+    w_Cf = o, o += (sizeof(T) == 4 ? 0 : kTS * NPT * 4);
     work_bytes = (o + 127) & ~127;
   }
 };
@@ -108,47 +110,65 @@ __global__ void __launch_bounds__((kMaxScanWarps + kHelperWarps) * 32) scan_fwd_
       unsigned char* wbase = work_base + (size_t)ws * lay.work_bytes;
       unsigned char* rbase = raw_base + (size_t)rslot * lay.raw_bytes;
       const float2* dlu = reinterpret_cast<const float2*>(wbase + lay.w_dlu) + lane;
-      // B / C are read from the raw (cp.async) tiles in their storage dtype; bf16 is widened in registers (two
-      // ALU ops per pair on the otherwise idle integer pipe) so that no helper round trip sits between the load
-      // landing and the scan using it
-      const T* Bf = reinterpret_cast<const T*>(rbase + lay.raw_B) + s * NPER;
-      const T* Cf = reinterpret_cast<const T*>(rbase + lay.raw_C) + s * NPER;
+      // B / C as fp32: the raw cp.async tile (fp32 I/O) or the copy widened by the helpers' pre-pass (bf16 I/O;
+      // widening in the scan warps costs 16 issue slots per thread and step, a third of this loop)
+      const float* Bf = (sizeof(T) == 4 ? reinterpret_cast<const float*>(rbase + lay.raw_B)
+                                        : reinterpret_cast<const float*>(wbase + lay.w_Bf)) + s * NPER;
+      const float* Cf = (sizeof(T) == 4 ? reinterpret_cast<const float*>(rbase + lay.raw_C)
+                                        : reinterpret_cast<const float*>(wbase + lay.w_Cf)) + s * NPER;
       float* yp = reinterpret_cast<float*>(wbase + lay.w_y) + (s * kTS) * kDT + lane;
       bar_sync(1 + ws, bar_count);  // stage c prepared
       // Operands of timestep t+1 are fetched BEFORE timestep t is computed and stored: ptxas will not move a
       // shared load above an earlier shared store it cannot disambiguate.
-      float2 dd_cur, dd_nxt;
+      // Software pipeline: (delta, delta*u) is fetched two steps ahead, B / C one step ahead, and the decay
+      // a_{t+1} = exp2(delta_{t+1} * A) is formed while step t's multiply-adds run, so that the MUFU results are
+      // never waited for.
+      float2 dd_cur, dd_nxt, dd_n2;
       float4 Bc[NPER / 4], Cc[NPER / 4], Bn[NPER / 4], Cn[NPER / 4];
-      auto fetch = [&](int t, float2& dd, float4 (&Bv)[NPER / 4], float4 (&Cv)[NPER / 4]) {
-        dd = dlu[t * kDT];
+      float2 a_cur[NPER / 2], a_nxt[NPER / 2];
+      auto fetch_bc = [&](int t, float4 (&Bv)[NPER / 4], float4 (&Cv)[NPER / 4]) {
 #pragma unroll
         for (int q = 0; q < NPER / 4; ++q) {
           Bv[q] = ld4_as_f32(Bf + t * NPT + 4 * q);
           Cv[q] = ld4_as_f32(Cf + t * NPT + 4 * q);
         }
       };
-      fetch(0, dd_cur, Bc, Cc);
+      auto decay = [&](const float2 dd, float2 (&a)[NPER / 2]) {
+        const float2 dl2 = make_float2(dd.x, dd.x);
+#pragma unroll
+        for (int k = 0; k < NPER / 2; ++k) {
+          const float2 gk = __fmul2_rn(dl2, A2[k]);
+          a[k] = make_float2(ex2_approx(gk.x), ex2_approx(gk.y));
+        }
+      };
+      dd_cur = dlu[0];
+      dd_nxt = dlu[(kTS > 1 ? 1 : 0) * kDT];
+      fetch_bc(0, Bc, Cc);
+      decay(dd_cur, a_cur);
 #pragma unroll
       for (int t = 0; t < kTS; ++t) {
-        if (t + 1 < kTS) fetch(t + 1, dd_nxt, Bn, Cn);
-        const float2 dl2 = make_float2(dd_cur.x, dd_cur.x), du2 = make_float2(dd_cur.y, dd_cur.y);
+        if (t + 2 < kTS) dd_n2 = dlu[(t + 2) * kDT];
+        if (t + 1 < kTS) {
+          fetch_bc(t + 1, Bn, Cn);
+          decay(dd_nxt, a_nxt);
+        }
+        const float2 du2 = make_float2(dd_cur.y, dd_cur.y);
         float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
         for (int q = 0; q < NPER / 4; ++q) {
           const float2 B01 = make_float2(Bc[q].x, Bc[q].y), B23 = make_float2(Bc[q].z, Bc[q].w);
           const float2 C01 = make_float2(Cc[q].x, Cc[q].y), C23 = make_float2(Cc[q].z, Cc[q].w);
-          const float2 g0 = __fmul2_rn(dl2, A2[2 * q]), g1 = __fmul2_rn(dl2, A2[2 * q + 1]);
-          const float2 a0 = make_float2(ex2_approx(g0.x), ex2_approx(g0.y));
-          const float2 a1 = make_float2(ex2_approx(g1.x), ex2_approx(g1.y));
-          h[2 * q] = __ffma2_rn(a0, h[2 * q], __fmul2_rn(du2, B01));
-          h[2 * q + 1] = __ffma2_rn(a1, h[2 * q + 1], __fmul2_rn(du2, B23));
+          h[2 * q] = __ffma2_rn(a_cur[2 * q], h[2 * q], __fmul2_rn(du2, B01));
+          h[2 * q + 1] = __ffma2_rn(a_cur[2 * q + 1], h[2 * q + 1], __fmul2_rn(du2, B23));
           acc = __ffma2_rn(h[2 * q], C01, acc);
           acc = __ffma2_rn(h[2 * q + 1], C23, acc);
         }
         sts_f32(yp + t * kDT, acc.x + acc.y);
-        dd_cur = dd_nxt;
+        dd_cur = dd_nxt, dd_nxt = dd_n2;
 #pragma unroll
         for (int q = 0; q < NPER / 4; ++q) Bc[q] = Bn[q], Cc[q] = Cn[q];
+#pragma unroll
+        for (int k = 0; k < NPER / 2; ++k) a_cur[k] = a_nxt[k];
         if ((t + 1) % CKI == 0) {
           // h is now the state at the start of checkpoint chunk (c*kTS + t + 1) / CKI
           const int tg_next = c * kTS + t + 1;
@@ -293,6 +313,16 @@ __global__ void __launch_bounds__((kMaxScanWarps + kHelperWarps) * 32) scan_fwd_
     float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float2*>(wbase + lay.w_dlu) + my_t * kDT + my_c);
     dst[0] = make_float4(r[0], r[1], r[2], r[3]);
     dst[1] = make_float4(r[4], r[5], r[6], r[7]);
+    if (sizeof(T) != 4) {
+      const T* sB = reinterpret_cast<const T*>(rbase + lay.raw_B);
+      const T* sC = reinterpret_cast<const T*>(rbase + lay.raw_C);
+      float* Bf = reinterpret_cast<float*>(wbase + lay.w_Bf);
+      float* Cf = reinterpret_cast<float*>(wbase + lay.w_Cf);
+      for (int i = ht; i < kTS * NPT / 8; i += kHelperThreads) {  // NPT is a multiple of 8
+        cvt8_bf16_f32(sB + 8 * i, Bf + 8 * i);
+        cvt8_bf16_f32(sC + 8 * i, Cf + 8 * i);
+      }
+    }
   };
 
   auto post_pass = [&](int c, int rslot) {
