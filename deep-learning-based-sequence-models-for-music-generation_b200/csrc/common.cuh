@@ -171,6 +171,32 @@ __device__ __forceinline__ void load_tile_async(T* __restrict__ s, int cols_s, c
   }
 }
 
+// Fixed-order column sums of a [nrows][ncols] fp32 partial buffer, for blocks of (32, 8) threads: thread (x, y) adds
+// rows y, y+8, ... of column blockIdx.x*32 + x (4 independent loads in flight), the 8 row groups are combined in
+// shared memory in a fixed order.  Returns the total on the threads with y == 0 (others: undefined).
+__device__ __forceinline__ float colsum_32x8(const float* __restrict__ ws, int nrows, int64_t row_stride, int col, bool ok) {
+  __shared__ float part[8][33];
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (ok) {
+    int r = threadIdx.y;
+    for (; r + 24 < nrows; r += 32) {
+      a0 += ws[(int64_t)r * row_stride + col];
+      a1 += ws[(int64_t)(r + 8) * row_stride + col];
+      a2 += ws[(int64_t)(r + 16) * row_stride + col];
+      a3 += ws[(int64_t)(r + 24) * row_stride + col];
+    }
+    for (; r < nrows; r += 8) a0 += ws[(int64_t)r * row_stride + col];
+  }
+  part[threadIdx.y][threadIdx.x] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  float s = 0.f;
+  if (threadIdx.y == 0) {
+#pragma unroll
+    for (int y = 0; y < 8; ++y) s += part[y][threadIdx.x];
+  }
+  return s;
+}
+
 __host__ __device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }

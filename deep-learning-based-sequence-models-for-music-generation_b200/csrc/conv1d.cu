@@ -10,7 +10,10 @@
 
 namespace mb {
 
-constexpr int kConvTS = 32;      // timesteps per thread segment
+constexpr int kConvTS = 8;       // timesteps per thread segment: short segments whose rows are ALL loaded up front
+                                 // (clamped addresses, no control dependence), so that every thread has its
+                                 // whole working set in flight and there are enough threads per SM to cover HBM
+                                 // latency; the K-1 halo rows are L1/L2 hits (neighbouring segments)
 constexpr int kConvWarps = 8;    // segments per block
 
 struct ConvParams {
@@ -56,6 +59,18 @@ struct Vec<T, 1> {
   static __device__ __forceinline__ void st(T* p, const float (&v)[1]) { IO<T>::st(p, v[0]); }
 };
 
+// One row of a thread's tile: loaded unconditionally from a clamped timestep (so that all of a thread's loads
+// are independent of each other and of any branch) and zeroed afterwards if the timestep is outside [0, L).
+template <typename T, int VEC>
+__device__ __forceinline__ void ld_row_clamped(const T* base, int64_t ls, int t, int L, float (&v)[VEC]) {
+  const int tc = min(max(t, 0), L - 1);
+  Vec<T, VEC>::ld(base + (int64_t)tc * ls, v);
+  if (t < 0 || t >= L) {
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) v[e] = 0.f;
+  }
+}
+
 // grid: (ceil(D/VEC/32), ceil(nseg/kConvWarps), B); block: (32, kConvWarps)
 template <typename T, int VEC, int K>
 __global__ void __launch_bounds__(32 * kConvWarps) conv_fwd_kernel(const ConvParams p) {
@@ -74,33 +89,23 @@ __global__ void __launch_bounds__(32 * kConvWarps) conv_fwd_kernel(const ConvPar
 #pragma unroll
     for (int k = 0; k < K; ++k) w[k][v] = p.w[(int64_t)(dv + v) * K + k];
   }
-  float win[K][VEC];  // win[k] = x[t - (K-1) + k]
+  float xr[kConvTS + K - 1][VEC];  // xr[i] = x[t0 - (K-1) + i]
 #pragma unroll
-  for (int k = 0; k < K - 1; ++k) {
-    const int t = t0 - (K - 1) + k;
-    if (t >= 0) {
-      Vec<T, VEC>::ld(x + (int64_t)t * p.x_ls, win[k + 1]);
-    } else {
+  for (int i = 0; i < kConvTS + K - 1; ++i) ld_row_clamped<T, VEC>(x, p.x_ls, t0 - (K - 1) + i, p.L, xr[i]);
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) win[k + 1][v] = 0.f;
+  for (int i = 0; i < kConvTS; ++i) {
+    const int t = t0 + i;
+    if (t < t1) {
+      float o[VEC];
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        float acc = bias[v];
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc = fmaf(w[k][v], xr[i + k][v], acc);
+        o[v] = silu_fast(acc);
+      }
+      Vec<T, VEC>::st(out + (int64_t)t * p.out_ls, o);
     }
-  }
-#pragma unroll 4
-  for (int t = t0; t < t1; ++t) {
-#pragma unroll
-    for (int k = 0; k < K - 1; ++k)
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) win[k][v] = win[k + 1][v];
-    Vec<T, VEC>::ld(x + (int64_t)t * p.x_ls, win[K - 1]);
-    float o[VEC];
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) {
-      float acc = bias[v];
-#pragma unroll
-      for (int k = 0; k < K; ++k) acc = fmaf(w[k][v], win[k][v], acc);
-      o[v] = silu_f(acc);
-    }
-    Vec<T, VEC>::st(out + (int64_t)t * p.out_ls, o);
   }
   if (p.final_state != nullptr && t1 == p.L) {
     // conv_state[b, d, k] = x[b, L-K+k, d] (zero where L-K+k < 0); win holds x[L-K .. L-1] unless the
@@ -150,60 +155,42 @@ __global__ void __launch_bounds__(32 * kConvWarps) conv_bwd_kernel(const ConvPar
 #pragma unroll
       for (int k = 0; k < K; ++k) w[k][v] = p.w[(int64_t)(dv + v) * K + k];
     }
-    float win[K][VEC];   // x[tt-(K-1) .. tt]
-    float dwin[K][VEC];  // dpre[tt-(K-1) .. tt]
+    // rows needed: x[t0-(K-1) .. t1+K-2] and dout[t0 .. t1+K-2] (dx[t] needs dpre[t .. t+K-1])
+    constexpr int NX = kConvTS + 2 * (K - 1), ND = kConvTS + K - 1;
+    float xr[NX][VEC], dp[ND][VEC];
 #pragma unroll
-    for (int k = 0; k < K; ++k)
+    for (int i = 0; i < NX; ++i) ld_row_clamped<T, VEC>(x, p.x_ls, t0 - (K - 1) + i, p.L, xr[i]);
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) dwin[k][v] = 0.f;
+    for (int i = 0; i < ND; ++i) ld_row_clamped<T, VEC>(dout, p.dout_ls, t0 + i, p.L, dp[i]);
+    // dpre[tt] = dout[tt] * silu'(pre[tt]) in place (rows past L are zero: dout was zeroed)
 #pragma unroll
-    for (int k = 0; k < K - 1; ++k) {
-      const int t = t0 - (K - 1) + k;
-      if (t >= 0) {
-        Vec<T, VEC>::ld(x + (int64_t)t * p.x_ls, win[k + 1]);
-      } else {
+    for (int i = 0; i < ND; ++i) {
+      const bool own = t0 + i < t1;  // own timestep: contributes to the parameter gradients exactly once
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) win[k + 1][v] = 0.f;
+      for (int v = 0; v < VEC; ++v) {
+        float pre = bias[v];
+#pragma unroll
+        for (int k = 0; k < K; ++k) pre = fmaf(w[k][v], xr[i + k][v], pre);
+        const float sg = rcp_approx(1.f + ex2_approx(-pre * kLog2e));
+        const float d = dp[i][v] * sg * fmaf(pre, 1.f - sg, 1.f);
+        dp[i][v] = d;
+        if (own) {
+          dbacc[v] += d;
+#pragma unroll
+          for (int k = 0; k < K; ++k) dwacc[k][v] = fmaf(d, xr[i + k][v], dwacc[k][v]);
+        }
       }
     }
-    // walk tt over the segment plus a K-1 look-ahead halo (dx[t] needs dpre[t .. t+K-1])
-    const int tend = t1 + (K - 1);
-#pragma unroll 2
-    for (int tt = t0; tt < tend; ++tt) {
 #pragma unroll
-      for (int k = 0; k < K - 1; ++k)
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) win[k][v] = win[k + 1][v], dwin[k][v] = dwin[k + 1][v];
-      if (tt < p.L) {
-        Vec<T, VEC>::ld(x + (int64_t)tt * p.x_ls, win[K - 1]);
-        float go[VEC];
-        Vec<T, VEC>::ld(dout + (int64_t)tt * p.dout_ls, go);
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) {
-          float pre = bias[v];
-#pragma unroll
-          for (int k = 0; k < K; ++k) pre = fmaf(w[k][v], win[k][v], pre);
-          const float sg = sigmoid_f(pre);
-          const float dp = go[v] * sg * fmaf(pre, 1.f - sg, 1.f);
-          dwin[K - 1][v] = dp;
-          if (tt < t1) {  // own timestep: contributes to the parameter gradients exactly once
-            dbacc[v] += dp;
-#pragma unroll
-            for (int k = 0; k < K; ++k) dwacc[k][v] = fmaf(dp, win[k][v], dwacc[k][v]);
-          }
-        }
-      } else {
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) dwin[K - 1][v] = 0.f;
-      }
-      const int to = tt - (K - 1);  // dx[to] = sum_k w[k] * dpre[to + (K-1) - k] = sum_k w[k] * dwin[K-1-k]
-      if (to >= t0) {
+    for (int i = 0; i < kConvTS; ++i) {
+      const int to = t0 + i;  // dx[to] = sum_k w[k] * dpre[to + (K-1) - k]
+      if (to < t1) {
         float o[VEC];
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
           float acc = 0.f;
 #pragma unroll
-          for (int k = 0; k < K; ++k) acc = fmaf(w[k][v], dwin[K - 1 - k][v], acc);
+          for (int k = 0; k < K; ++k) acc = fmaf(w[k][v], dp[i + (K - 1) - k][v], acc);
           o[v] = acc;
         }
         Vec<T, VEC>::st(dx + (int64_t)to * p.dx_ls, o);
@@ -232,14 +219,15 @@ __global__ void __launch_bounds__(32 * kConvWarps) conv_bwd_kernel(const ConvPar
   }
 }
 
+// grid: ceil((K+1)*D / 32) blocks of (32, 8) threads
 template <int K>
 __global__ void conv_bwd_finalize_kernel(const ConvParams p) {
   const int nrow = p.B * p.nsegblk;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (int64_t)(K + 1) * p.D;
-       i += (int64_t)gridDim.x * blockDim.x) {
+  const int64_t i = (int64_t)blockIdx.x * 32 + threadIdx.x;  // column of the [nrow][(K+1)*D] partial buffer
+  const bool ok = i < (int64_t)(K + 1) * p.D;
+  const float s = colsum_32x8(p.ws, nrow, (int64_t)(K + 1) * p.D, (int)i, ok);
+  if (ok && threadIdx.y == 0) {
     const int k = (int)(i / p.D), d = (int)(i % p.D);
-    float s = 0.f;
-    for (int r = 0; r < nrow; ++r) s += p.ws[(int64_t)r * (K + 1) * p.D + i];
     if (k < K)
       p.dw[(int64_t)d * K + k] = s;
     else if (p.dbias)
@@ -260,7 +248,7 @@ static int launch_conv(const ConvParams& p, bool bwd, cudaStream_t st) {
   count_launch();
   int rc = check_launch("conv1d_silu_bwd");
   if (rc) return rc;
-  conv_bwd_finalize_kernel<K><<<ceil_div((K + 1) * p.D, 256), 256, 0, st>>>(p);
+  conv_bwd_finalize_kernel<K><<<ceil_div((K + 1) * p.D, 32), dim3(32, 8), 0, st>>>(p);
   count_launch();
   return check_launch("conv1d_silu_bwd_finalize");
 }

@@ -129,8 +129,20 @@ __global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const NormParams p) {
     const T* dy = static_cast<const T*>(p.dy) + row * p.dim;
     const TR* dres = p.dres ? static_cast<const TR*>(p.dres) + row * p.dim : nullptr;
     const float rstd = p.rstd[row];
-    float rh[G][V], g[G][V];
+    // Rows of up to 1024 columns: the incoming residual gradient is fetched with the other two operands (one DRAM
+    // round trip per row, not two); wider rows load it late to stay inside the register budget.
+    constexpr bool kEarly = G * V <= 32;
+    float rh[G][V], g[G][V], dr[kEarly ? G : 1][V];
     float dot = 0.f;
+    if constexpr (kEarly) {
+#pragma unroll
+      for (int k = 0; k < G; ++k) {
+        const int c = (lane + 32 * k) * V;
+#pragma unroll
+        for (int e = 0; e < V; ++e) dr[k][e] = 0.f;
+        if (dres && c < p.dim) Row<TR, V>::ld(dres + c, dr[k]);
+      }
+    }
 #pragma unroll
     for (int k = 0; k < G; ++k) {
       const int c = (lane + 32 * k) * V;
@@ -157,11 +169,14 @@ __global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const NormParams p) {
         float o[V];
 #pragma unroll
         for (int e = 0; e < V; ++e) o[e] = rstd * (g[k][e] - rh[k][e] * dot);
-        if (dres) {
-          float dr[V];
-          Row<TR, V>::ld(dres + c, dr);
+        if constexpr (kEarly) {
 #pragma unroll
-          for (int e = 0; e < V; ++e) o[e] += dr[e];
+          for (int e = 0; e < V; ++e) o[e] += dr[k][e];
+        } else if (dres) {
+          float dl[V];
+          Row<TR, V>::ld(dres + c, dl);
+#pragma unroll
+          for (int e = 0; e < V; ++e) o[e] += dl[e];
         }
         if (p.dx) Row<T, V>::st(static_cast<T*>(p.dx) + row * p.dim + c, o);
         if (p.dres_out) Row<TR, V>::st(static_cast<TR*>(p.dres_out) + row * p.dim + c, o);
@@ -181,12 +196,12 @@ __global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const NormParams p) {
   }
 }
 
+// grid: ceil(dim / 32) blocks of (32, 8) threads
 __global__ void rmsnorm_bwd_finalize_kernel(const NormParams p) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= p.dim) return;
-  float s = 0.f;
-  for (int b = 0; b < p.nblocks; ++b) s += p.ws[(int64_t)b * p.dim + c];
-  p.dw[c] = s;
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const bool ok = c < p.dim;
+  const float s = colsum_32x8(p.ws, p.nblocks, p.dim, c, ok);
+  if (ok && threadIdx.y == 0) p.dw[c] = s;
 }
 
 static int norm_blocks(int64_t rows) {
@@ -211,7 +226,7 @@ static int norm_launch_g(const NormParams& p, bool bwd, cudaStream_t st) {
   count_launch();
   int rc = check_launch("rmsnorm_bwd");
   if (rc) return rc;
-  rmsnorm_bwd_finalize_kernel<<<ceil_div(p.dim, 256), 256, 0, st>>>(p);
+  rmsnorm_bwd_finalize_kernel<<<ceil_div(p.dim, 32), dim3(32, 8), 0, st>>>(p);
   count_launch();
   return check_launch("rmsnorm_bwd_finalize");
 }
