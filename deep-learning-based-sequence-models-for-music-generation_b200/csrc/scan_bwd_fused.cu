@@ -312,7 +312,7 @@ __global__ void __launch_bounds__((NW + kBHelperWarps) * 32, 1) scan_bwd_fused_k
       uint32_t ha = hs0 + (par ? 0 : (K - 1) * Lay::hs_slot);          // hs slot read (and then rewritten)
       const int hstep = par ? Lay::hs_slot : -Lay::hs_slot;
       uint32_t sa = st0 + oslot + (kCK - 2) * kRowC;                   // state sums of step 2tp
-      uint32_t pa = pb0 + oslot + (kCK - 2) * RS * 4;                  // dB|dC flush base of step 2tp (tp & 3 == 0)
+      uint32_t pa = pb0 + oslot + kCK * RS * 4;                        // dB|dC flush base: 8 steps down per flush
       // delta of the first iteration's four steps (the MUFU inputs), prefetched one iteration ahead from here on
       float2 dl1 = lds64(va + Lay::w_dl + kRowC), dl0 = lds64(va + Lay::w_dl);
       float2 dle = lds64(ra + Lay::w_dl), dlo = lds64(ra + Lay::w_dl + kRowC);
@@ -344,31 +344,37 @@ __global__ void __launch_bounds__((NW + kBHelperWarps) * 32, 1) scan_bwd_fused_k
         }
         pend0 = rev_compute(dl0, du0, dy0, B0, C0, he, false, g == col);
         pend_addr = sa;
-        if ((tp & 3) == 0) {
-          // flush 8 timesteps of dB | dC: this thread holds steps 2tp + 2*t4 (+1), states n0..n0+3
-          sts128(pa, make_float4(accB[0][0], accB[0][2], accB[1][0], accB[1][2]));
-          sts128(pa + RS * 4, make_float4(accB[0][1], accB[0][3], accB[1][1], accB[1][3]));
-          sts128(pa + NPT * 4, make_float4(accC[0][0], accC[0][2], accC[1][0], accC[1][2]));
-          sts128(pa + (RS + NPT) * 4, make_float4(accC[0][1], accC[0][3], accC[1][1], accC[1][3]));
-#pragma unroll
-          for (int w = 0; w < 2; ++w)
-#pragma unroll
-            for (int k = 0; k < 4; ++k) accB[w][k] = accC[w][k] = 0.f;
-        }
         // advance; prefetch the next iteration's delta (past the chunk on the last iteration: in-bounds, unused)
-        va -= 2 * kRowC, vb -= 2 * kRowS, sa -= 2 * kRowC, pa -= 2 * RS * 4, ha += hstep;
+        va -= 2 * kRowC, vb -= 2 * kRowS, sa -= 2 * kRowC, ha += hstep;
         dl1 = lds64(va + Lay::w_dl + kRowC), dl0 = lds64(va + Lay::w_dl);
         if constexpr (kRec) {
           ra += 2 * kRowC, rb += 2 * kRowS;
           dle = lds64(ra + Lay::w_dl), dlo = lds64(ra + Lay::w_dl + kRowC);
         }
       };
-      if (has_next) {
+      // four step pairs (8 timesteps) fill the accumulator columns; then flush dB | dC: this thread holds steps
+      // 8*grp' + 2*t4 (+1), states n0..n0+3
+      auto flush = [&]() {
+        pa -= 8 * RS * 4;
+        sts128(pa, make_float4(accB[0][0], accB[0][2], accB[1][0], accB[1][2]));
+        sts128(pa + RS * 4, make_float4(accB[0][1], accB[0][3], accB[1][1], accB[1][3]));
+        sts128(pa + NPT * 4, make_float4(accC[0][0], accC[0][2], accC[1][0], accC[1][2]));
+        sts128(pa + (RS + NPT) * 4, make_float4(accC[0][1], accC[0][3], accC[1][1], accC[1][3]));
+#pragma unroll
+        for (int w = 0; w < 2; ++w)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) accB[w][k] = accC[w][k] = 0.f;
+      };
 #pragma unroll 1
-        for (int i = 0; i < K; ++i) body(i, std::true_type{});
-      } else {
+      for (int grp = 0; grp < K / 4; ++grp) {
+        if (has_next) {
 #pragma unroll 1
-        for (int i = 0; i < K; ++i) body(i, std::false_type{});
+          for (int j = 0; j < 4; ++j) body(4 * grp + j, std::true_type{});
+        } else {
+#pragma unroll 1
+          for (int j = 0; j < 4; ++j) body(4 * grp + j, std::false_type{});
+        }
+        flush();
       }
       finish_pending();  // the results of this iteration must be complete before DONE
       pend_addr = 0;

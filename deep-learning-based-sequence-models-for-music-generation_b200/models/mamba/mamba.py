@@ -69,6 +69,46 @@ def _act_dtype(x: torch.Tensor) -> torch.dtype:
     return x.dtype
 
 
+class _LinearFn(torch.autograd.Function):
+    """y = x @ W^T in the autocast dtype (cuBLAS plumbing, no arithmetic of its own).  Unlike nn.Linear under
+    autocast, the weight gradient leaves the GEMM already in the parameter's dtype (bf16 x bf16 -> fp32 output)
+    instead of as a bf16 product followed by a separate widening pass over every weight matrix."""
+
+    @staticmethod
+    def forward(ctx, x, w, dt):
+        wc = w.to(dt)
+        x2 = x.reshape(-1, x.shape[-1])
+        if x2.dtype != dt:
+            x2 = x2.to(dt)
+        out = torch.mm(x2, wc.t())
+        ctx.save_for_backward(x2, wc)
+        ctx.meta = (x.shape, x.dtype, w.dtype)
+        return out.view(*x.shape[:-1], w.shape[0])
+
+    @staticmethod
+    def backward(ctx, g):
+        x2, wc = ctx.saved_tensors
+        xshape, xdt, wdt = ctx.meta
+        g2 = g.reshape(-1, g.shape[-1])
+        if g2.dtype != wc.dtype:
+            g2 = g2.to(wc.dtype)
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.mm(g2, wc).view(xshape)
+            if dx.dtype != xdt:
+                dx = dx.to(xdt)
+        if ctx.needs_input_grad[1]:
+            dw = torch.mm(g2.t(), x2) if wdt == g2.dtype else torch.mm(g2.t(), x2, out_dtype=wdt)
+        return dx, dw, None
+
+
+def _linear(x, weight, bias=None):
+    """F.linear; on CUDA under autocast (and without a bias) through _LinearFn."""
+    if bias is None and x.is_cuda and torch.is_autocast_enabled("cuda"):
+        return _LinearFn.apply(x, weight, torch.get_autocast_dtype("cuda"))
+    return F.linear(x, weight, bias)
+
+
 def _linear_step(x, lin):
     """nn.Linear for one position per sequence: the weight-streaming kernel for <= 16 rows, cuBLAS otherwise."""
     if x.shape[0] <= 16 and x.shape[1] % 4 == 0 and lin.weight.is_contiguous():
@@ -109,16 +149,16 @@ class MambaBlock(nn.Module):  # simple_mamba @L184
     # ---- training / full-sequence forward (@L228-245 with ssm @L263-280 and selective_scan @L310-333) --
     def forward(self, x):
         p = self.params
-        xz = self.in_proj(x)                                              # @L230  [B, L, 2*d_inner]
+        xz = _linear(x, self.in_proj.weight, self.in_proj.bias)           # @L230  [B, L, 2*d_inner]
         xs, res = xz.split([p.d_inner, p.d_inner], dim=-1)                # @L231  views, no copy
         xc = ops.causal_conv1d_silu_fn(xs, self.conv1d.weight, self.conv1d.bias)   # @L233-237 (one kernel)
         A = -torch.exp(self.A_log.float())                                # @L270
-        x_dbl = self.x_proj(xc)                                           # @L273
+        x_dbl = _linear(xc, self.x_proj.weight)                           # @L273
         dt_r, Bm, Cm = x_dbl.split([p.dt_rank, p.d_state, p.d_state], dim=-1)  # @L275 views
-        dt_raw = F.linear(dt_r, self.dt_proj.weight)                      # @L276: bias + softplus fused below
+        dt_raw = _linear(dt_r, self.dt_proj.weight)                       # @L276: bias + softplus fused below
         y = ops.selective_scan_fn(xc, dt_raw, A, Bm, Cm, self.D.float(), z=res,
                                   delta_bias=self.dt_proj.bias.float(), delta_softplus=True)  # @L276-278, @L241
-        return self.out_proj(y)                                           # @L243
+        return _linear(y, self.out_proj.weight, self.out_proj.bias)       # @L243
 
     # ---- inference: full-sequence forward that also leaves the recurrent state behind ---------------
     @torch.no_grad()
@@ -234,7 +274,7 @@ class _PaddedHeadFn(torch.autograd.Function):
             gp = torch.zeros((rows, Vp), dtype=wp.dtype, device=g.device)
             gp[:, :V].copy_(g.reshape(rows, V))
         dx = torch.mm(gp, wp).view(xshape).to(xdt)
-        dw = torch.mm(gp.t(), x2)[:V].to(wdt)
+        dw = (torch.mm(gp.t(), x2) if wdt == gp.dtype else torch.mm(gp.t(), x2, out_dtype=wdt))[:V]
         return dx, dw, None
 
 
