@@ -423,8 +423,16 @@ def main():
             per_kernel[name] = e
         dom = max((n for n in per_kernel if n in ab), key=lambda n: per_kernel[n]["mean_us"] * per_kernel[n]["launches_per_step"])
         d = per_kernel[dom]
+        # DRAM traffic of the dominant kernel per launch, from the committed ncu --set full capture of the same
+        # shape (only valid for the bf16 default workload it was taken on)
+        traffic = None
+        try:
+            if args.dtype == "bf16":
+                traffic = json.loads((ROOT / "profiles" / "r01_ncu_traffic.json").read_text())[dom]["traffic_bytes"]
+        except Exception:
+            traffic = None
         line["roofline"] = {"kernel": dom, "bound": "hbm", "achieved": d["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                            "frac": d["frac_of_hbm_peak"], "traffic": None, "peak_source": peak_src,
+                            "frac": d["frac_of_hbm_peak"], "traffic": traffic, "peak_source": peak_src,
                             "mean_us": d["mean_us"], "algorithmic_bytes": d["algorithmic_bytes"],
                             "binding_pipe": mufu_view(dom, B, T + cc.N_META, p.d_inner, p.d_state, d["mean_us"]),
                             "note": "d_state=64 makes this kernel MUFU/FMA-bound, not HBM-bound (SURVEY.md F8); "
