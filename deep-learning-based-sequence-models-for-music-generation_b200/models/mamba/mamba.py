@@ -69,6 +69,28 @@ def _act_dtype(x: torch.Tensor) -> torch.dtype:
     return x.dtype
 
 
+class AsyncWgrad:
+    """Weight-gradient GEMMs on a side stream.  The scan kernels put one CTA on 128 of the 148 SMs for most of the
+    backward; a weight gradient is needed only by the optimizer, so `_LinearFn.backward` can write it straight into
+    `param.grad` on a second stream, where it runs on the SMs the scans leave idle.  `join()` (before the
+    optimizer) makes the current stream wait for it.  Works eagerly and under CUDA-graph capture (the fork/join
+    becomes graph edges); off unless a Trainer turns it on."""
+    stream = None
+
+    @classmethod
+    def enable(cls, device):
+        cls.stream = torch.cuda.Stream(device=device)
+
+    @classmethod
+    def disable(cls):
+        cls.stream = None
+
+    @classmethod
+    def join(cls):
+        if cls.stream is not None:
+            torch.cuda.current_stream(cls.stream.device).wait_stream(cls.stream)
+
+
 class _LinearFn(torch.autograd.Function):
     """y = x @ W^T in the autocast dtype (cuBLAS plumbing, no arithmetic of its own).  Unlike nn.Linear under
     autocast, the weight gradient leaves the GEMM already in the parameter's dtype (bf16 x bf16 -> fp32 output)
@@ -83,6 +105,7 @@ class _LinearFn(torch.autograd.Function):
         out = torch.mm(x2, wc.t())
         ctx.save_for_backward(x2, wc)
         ctx.meta = (x.shape, x.dtype, w.dtype)
+        ctx.param = w if isinstance(w, nn.Parameter) else None
         return out.view(*x.shape[:-1], w.shape[0])
 
     @staticmethod
@@ -98,7 +121,17 @@ class _LinearFn(torch.autograd.Function):
             if dx.dtype != xdt:
                 dx = dx.to(xdt)
         if ctx.needs_input_grad[1]:
-            dw = torch.mm(g2.t(), x2) if wdt == g2.dtype else torch.mm(g2.t(), x2, out_dtype=wdt)
+            side, p = AsyncWgrad.stream, ctx.param
+            if (side is not None and p is not None and p.grad is not None and p.grad.dtype == wdt
+                    and p.grad.is_contiguous() and wdt != g2.dtype):
+                # straight into param.grad on the side stream (this layer is the parameter's only user)
+                cur = torch.cuda.current_stream(g2.device)
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    torch.mm(g2.t(), x2, out_dtype=wdt, out=p.grad)
+                g2.record_stream(side), x2.record_stream(side)
+            else:
+                dw = torch.mm(g2.t(), x2) if wdt == g2.dtype else torch.mm(g2.t(), x2, out_dtype=wdt)
         return dx, dw, None
 
 

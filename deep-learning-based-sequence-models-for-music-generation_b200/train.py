@@ -225,7 +225,8 @@ class Trainer:
     # on CPU/gloo (tests/test_dist_cpu.py); under NCCL + CUDA-graph capture it hung on the 2-GPU box in round 1, so
     # the default is the plain post-backward exchange (92-97 % weak-scaling efficiency at 8 GPUs as measured).
     def __init__(self, model, lr=None, autocast_dtype=torch.bfloat16, world_size=1, process_group=None,
-                 batch_size=None, block_len=None, use_graph=True, bucket_mb=64, overlap_allreduce=False):
+                 batch_size=None, block_len=None, use_graph=True, bucket_mb=64, overlap_allreduce=False,
+                 async_wgrad=None):
         self.model = model
         self.device = next(model.parameters()).device
         self.autocast_dtype = autocast_dtype
@@ -238,6 +239,25 @@ class Trainer:
         self.meta = torch.zeros(B, cc.N_META, dtype=torch.long, device=self.device)
         self.loss = torch.zeros((), device=self.device)
         self._flatten_grads(bucket_mb)
+        # weight-gradient GEMMs of the mixer's linear layers on a side stream (models.mamba.AsyncWgrad): needs
+        # autocast (the fp32-output GEMM path) and gradient buffers that exist before backward
+        # (default: on for single-GPU training; measured +1 % — cuBLAS's 2-CTA-cluster GEMMs find few free TPCs
+        # next to the scans — and not yet exercised together with the NCCL exchange, so off for world_size > 1)
+        if async_wgrad is None:
+            async_wgrad = os.environ.get("MAMBA_B200_ASYNC_WGRAD", "1" if world_size == 1 else "0") == "1"
+        self.async_wgrad = bool(async_wgrad) and self.device.type == "cuda" and autocast_dtype is not None
+        self._wgrad_params = []
+        if self.async_wgrad:
+            from .models.mamba.mamba import AsyncWgrad, MambaBlock
+            AsyncWgrad.enable(self.device)
+            for m in model.modules():
+                if isinstance(m, MambaBlock):
+                    for lin in (m.in_proj, m.x_proj, m.dt_proj, m.out_proj):
+                        if lin.bias is None or lin is m.dt_proj:
+                            self._wgrad_params.append(lin.weight)
+            if self.grads is None:
+                for p in self._wgrad_params:
+                    p.grad = torch.zeros_like(p)
         self.overlap = overlap_allreduce and world_size > 1
         if self.overlap:
             self.grads.overlap_with_backward(world_size, process_group)
@@ -264,10 +284,16 @@ class Trainer:
             output = self.model(self.src, self.meta)
         loss = loss_fn(self.src, self.trg, output)
         if self.grads is None:
+            keep = [p.grad for p in self._wgrad_params]       # overwritten (not accumulated) by the side-stream GEMMs
             self.optimizer.zero_grad(set_to_none=True)
+            for p, g in zip(self._wgrad_params, keep):
+                p.grad = g
         else:
             self.grads.zero()
         loss.backward()
+        if self.async_wgrad:
+            from .models.mamba.mamba import AsyncWgrad
+            AsyncWgrad.join()
         self._allreduce()
         self.optimizer.step()
         self.loss.copy_(loss.detach())

@@ -198,6 +198,33 @@ def test_trainer_graph_step_equals_eager_step():
         assert_close(p2, p1, 1e-3, 1e-4, what=f"param {n1} after 4 steps")
 
 
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_side_stream_weight_gradients_equal_inline_ones(use_graph):
+    """bf16-autocast training steps with the weight-gradient GEMMs on the side stream (AsyncWgrad, written straight
+    into param.grad) and with them inline: same losses, same parameters after 3 Adam steps (same GEMMs, same
+    inputs -> bit-identical)."""
+    from mamba_b200 import synthetic, train
+    from mamba_b200.models.mamba import Mamba, ModelArgs
+    from mamba_b200.models.mamba.mamba import AsyncWgrad
+    torch.manual_seed(0)
+    a = Mamba(_args(ModelArgs, d_model=128, d_state=64)).cuda()
+    b = Mamba(_args(ModelArgs, d_model=128, d_state=64)).cuda()
+    b.load_state_dict(a.state_dict())
+    try:
+        ta = train.Trainer(a, lr=1e-3, batch_size=2, block_len=48, use_graph=use_graph, async_wgrad=False)
+        assert AsyncWgrad.stream is None or not ta.async_wgrad
+        AsyncWgrad.disable()
+        la = [ta.step(*(t.cuda() for t in synthetic.batch(2, 48, seed=30 + i))).item() for i in range(3)]
+        tb = train.Trainer(b, lr=1e-3, batch_size=2, block_len=48, use_graph=use_graph, async_wgrad=True)
+        assert tb.async_wgrad and AsyncWgrad.stream is not None and len(tb._wgrad_params) == 4 * 2
+        lb = [tb.step(*(t.cuda() for t in synthetic.batch(2, 48, seed=30 + i))).item() for i in range(3)]
+    finally:
+        AsyncWgrad.disable()
+    assert la == lb, (la, lb)
+    for (n1, p1), (n2, p2) in zip(a.named_parameters(), b.named_parameters()):
+        assert torch.equal(p1, p2), f"param {n1} differs between inline and side-stream weight gradients"
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("padded", [False, True])
 def test_fused_loss_matches_oracle_loss(dtype, padded):
