@@ -484,6 +484,46 @@ __global__ void scan_bwd_finalize_kernel(const ScanBwdParams p, int rows_per_blo
   if ((int)blockIdx.x < nrow_blocks) {
     const int64_t row0 = (int64_t)blockIdx.x * rows_per_block;  // row = b * L + t
     const int64_t nrows = (int64_t)p.B * p.L;
+    const int64_t ts = (int64_t)p.L * p.N;
+    if ((p.N & 3) == 0) {
+      // 4 states per thread: 16-byte loads of the per-tile partials, 8 of them in flight (4 interleaved partial
+      // sums per array, combined in a fixed order)
+      const int nq = p.N >> 2;
+      for (int i = tid; i < rows_per_block * nq; i += blockDim.x) {
+        const int64_t row = row0 + i / nq;
+        const int n = (i % nq) * 4;
+        if (row >= nrows) break;
+        const int b = (int)(row / p.L);
+        const int64_t t = row - (int64_t)b * p.L;
+        const float* sB = p.ws_dB + (((int64_t)b * p.ntiles) * p.L + t) * p.N + n;
+        const float* sC = p.ws_dC + (((int64_t)b * p.ntiles) * p.L + t) * p.N + n;
+        float4 aB[4], aC[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) aB[q] = aC[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        auto add4 = [](float4& a, const float4 v) { a.x += v.x, a.y += v.y, a.z += v.z, a.w += v.w; };
+        int k = 0;
+        for (; k + 4 <= p.ntiles; k += 4) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            add4(aB[q], __ldcs(reinterpret_cast<const float4*>(sB + (k + q) * ts)));
+            add4(aC[q], __ldcs(reinterpret_cast<const float4*>(sC + (k + q) * ts)));
+          }
+        }
+        for (; k < p.ntiles; ++k) {
+          add4(aB[0], __ldcs(reinterpret_cast<const float4*>(sB + k * ts)));
+          add4(aC[0], __ldcs(reinterpret_cast<const float4*>(sC + k * ts)));
+        }
+        const float rB[4] = {(aB[0].x + aB[1].x) + (aB[2].x + aB[3].x), (aB[0].y + aB[1].y) + (aB[2].y + aB[3].y),
+                             (aB[0].z + aB[1].z) + (aB[2].z + aB[3].z), (aB[0].w + aB[1].w) + (aB[2].w + aB[3].w)};
+        const float rC[4] = {(aC[0].x + aC[1].x) + (aC[2].x + aC[3].x), (aC[0].y + aC[1].y) + (aC[2].y + aC[3].y),
+                             (aC[0].z + aC[1].z) + (aC[2].z + aC[3].z), (aC[0].w + aC[1].w) + (aC[2].w + aC[3].w)};
+        T* oB = static_cast<T*>(p.dB) + (int64_t)b * p.dB_bs + t * p.dB_ls + n;
+        T* oC = static_cast<T*>(p.dC) + (int64_t)b * p.dC_bs + t * p.dC_ls + n;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) IO<T>::st(oB + e, rB[e]), IO<T>::st(oC + e, rC[e]);
+      }
+      return;
+    }
     const int nel = rows_per_block * p.N;
     for (int i = tid; i < nel; i += blockDim.x) {
       const int64_t row = row0 + i / p.N;
@@ -493,7 +533,6 @@ __global__ void scan_bwd_finalize_kernel(const ScanBwdParams p, int rows_per_blo
       const int64_t t = row - (int64_t)b * p.L;
       const float* sB = p.ws_dB + (((int64_t)b * p.ntiles) * p.L + t) * p.N + n;
       const float* sC = p.ws_dC + (((int64_t)b * p.ntiles) * p.L + t) * p.N + n;
-      const int64_t ts = (int64_t)p.L * p.N;
       // fixed-order sum with 8 loads in flight (4 interleaved partial sums, combined in a fixed order)
       float aB[4] = {0.f, 0.f, 0.f, 0.f}, aC[4] = {0.f, 0.f, 0.f, 0.f};
       int k = 0;
@@ -579,7 +618,7 @@ static int launch_bwd(const ScanBwdParams& p, cudaStream_t stream) {
 
 template <typename T>
 static int launch_finalize(const ScanBwdParams& p, cudaStream_t stream) {
-  const int rows_per_block = 8;
+  const int rows_per_block = (p.N & 3) == 0 ? 1024 / p.N > 0 ? 1024 / p.N : 1 : 8;  // 256 threads x 4 states each
   const int nrow_blocks = (int)(((int64_t)p.B * p.L + rows_per_block - 1) / rows_per_block);
   const int nsmall = ceil_div(p.D * p.N, 256 * 4);
   scan_bwd_finalize_kernel<T><<<nrow_blocks + nsmall, 256, 0, stream>>>(p, rows_per_block, nrow_blocks);
