@@ -484,3 +484,55 @@ def test_scan_forward_writes_stay_inside_their_buffers(shape):
     assert bool((out != SENT).all())
     ref = _oracle_scan({k: v.cpu() for k, v in t.items()})
     assert_close(out, ref, RTOL32, what=f"guarded scan fwd {shape}")
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(2, 37, 40, 64), (1, 50, 36, 32), (2, 129, 72, 64)])
+def test_scan_backward_writes_stay_inside_their_buffers(shape, dtype, variant, monkeypatch):
+    """Guard bands around everything the backward allocates (du, ddelta, dz, dB, dC, dA, dD, d_bias and the partial-sum
+    workspace) at ragged shapes, for both kernels: the sentinels on either side of each buffer must survive."""
+    import math
+    from mamba_b200 import ops
+    B, L, D, N = shape
+    t = scan_inputs(B, L, D, N, seed=13, dtype=dtype)
+    g = _leafs(t, "cuda")
+    out = ops.selective_scan_fn(g["u"], g["delta_raw"], g["A"], g["B"], g["C"], g["D"], z=g["z"],
+                                delta_bias=g["bias"], delta_softplus=True)
+    dout = torch.randn(B, L, D, generator=torch.Generator().manual_seed(3)).to(dtype).cuda()
+    arenas, pad = [], 64
+    real_empty = torch.empty
+
+    def guarded(shape_, dt, device):
+        n = math.prod(shape_)
+        a = real_empty(n + 2 * pad, dtype=dt, device=device)
+        a.fill_(0xA5 if dt == torch.uint8 else 12345.0)
+        arenas.append((a, n, a[:pad].clone()))
+        return a[pad:pad + n].view(*shape_)
+
+    def fake_empty(*size, dtype=None, device=None, **kw):
+        shape_ = tuple(size[0]) if len(size) == 1 and not isinstance(size[0], int) else tuple(size)
+        if device is None or torch.device(device).type != "cuda":
+            return real_empty(*size, dtype=dtype, device=device, **kw)
+        return guarded(shape_, dtype or torch.float32, device)
+
+    def fake_empty_like(x, **kw):
+        return guarded(tuple(x.shape), kw.get("dtype", x.dtype), x.device)
+
+    monkeypatch.setattr(torch, "empty", fake_empty)
+    monkeypatch.setattr(torch, "empty_like", fake_empty_like)
+    ops.SCAN_BWD_VARIANT = variant
+    try:
+        out.backward(dout)
+        torch.cuda.synchronize()
+    finally:
+        ops.SCAN_BWD_VARIANT = 0
+        monkeypatch.undo()
+    assert len(arenas) >= 9, f"only {len(arenas)} guarded allocations"
+    for a, n, sent in arenas:
+        assert torch.equal(a[:pad], sent) and torch.equal(a[pad + n:], sent), f"write outside a {n}-element buffer"
+    c = _leafs(t, "cpu")
+    _oracle_scan(c).backward(dout.float().cpu())
+    rtol, floor = (RTOL32, 1e-5) if dtype == torch.float32 else (RTOL16, FLOOR16)
+    for k in c:
+        assert_close(g[k].grad, c[k].grad, rtol, floor, what=f"guarded scan bwd d{k} {shape}", atol_abs=1e-6 if k == "A" else 0.0)

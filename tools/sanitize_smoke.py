@@ -11,7 +11,8 @@ from mamba_b200.models.mamba import Mamba, ModelArgs  # noqa: E402
 dev = torch.device("cuda")
 g = torch.Generator(device=dev).manual_seed(0)
 for (B, L, D, N, dt) in [(2, 37, 40, 5, torch.float32), (1, 100, 96, 64, torch.float32), (2, 70, 64, 32, torch.bfloat16),
-                         (1, 17, 36, 48, torch.float32), (2, 33, 64, 16, torch.bfloat16)]:
+                         (1, 17, 36, 48, torch.float32), (2, 33, 64, 16, torch.bfloat16),
+                         (2, 50, 72, 64, torch.bfloat16), (1, 21, 40, 64, torch.bfloat16)]:
     xz = torch.randn(B, L, 2 * D, device=dev, generator=g).to(dt).requires_grad_(True)
     xdbl = torch.randn(B, L, 4 + 2 * N, device=dev, generator=g).to(dt).requires_grad_(True)
     u, z = xz.split([D, D], dim=-1)
@@ -21,8 +22,11 @@ for (B, L, D, N, dt) in [(2, 37, 40, 5, torch.float32), (1, 100, 96, 64, torch.f
     Dv = torch.randn(D, device=dev, generator=g).requires_grad_(True)
     bias = torch.randn(D, device=dev, generator=g).requires_grad_(True)
     for chunk in (8, 16):
-        y = ops.selective_scan_fn(u, dl, A, Bm, Cm, Dv, z=z, delta_bias=bias, delta_softplus=True, chunk=chunk)
-        y.float().square().sum().backward()
+        for variant in ((0, 1) if N in (32, 64) else (0,)):   # 1: the fused backward, also with fp32 I/O
+            ops.SCAN_BWD_VARIANT = variant
+            y = ops.selective_scan_fn(u, dl, A, Bm, Cm, Dv, z=z, delta_bias=bias, delta_softplus=True, chunk=chunk)
+            y.float().square().sum().backward()
+    ops.SCAN_BWD_VARIANT = 0
     w = torch.randn(D, 1, 4, device=dev, generator=g).requires_grad_(True)
     cb = torch.randn(D, device=dev, generator=g).requires_grad_(True)
     c = ops.causal_conv1d_silu_fn(u, w, cb)
