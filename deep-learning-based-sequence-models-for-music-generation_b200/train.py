@@ -129,7 +129,12 @@ class FlatGrads:
     runs under the backward of the early ones (buckets complete in reverse layer order); `finish()` joins the side
     stream.  Both work under CUDA-graph capture (the side stream forks from / joins the capturing stream)."""
 
-    def __init__(self, params, bucket_mb=64):
+    def __init__(self, params, bucket_mb=64, groups=None):
+        """`groups` (optional): list of parameter lists — one bucket per group, laid out in that order (the staged
+        backward of Trainer reduces bucket i as soon as stage i's gradients exist); otherwise buckets of about
+        `bucket_mb` MiB in parameter order."""
+        if groups is not None:
+            params = [p for g in groups for p in g]
         self.params = [p for p in params if p.requires_grad]
         total = sum(p.numel() for p in self.params)
         dev = self.params[0].device
@@ -138,11 +143,17 @@ class FlatGrads:
         # buckets end on parameter boundaries so that "bucket complete" is a count of parameters
         self.buckets, self._bucket_of = [], {}
         off, start, members = 0, 0, []
-        for p in self.params:
+        ends = None
+        if groups is not None:
+            ends, acc = set(), 0
+            for g in groups:
+                acc += sum(1 for p in g if p.requires_grad)
+                ends.add(acc)
+        for k, p in enumerate(self.params):
             p.grad = self.flat[off:off + p.numel()].view_as(p)
             off += p.numel()
             members.append(p)
-            if off - start >= per:
+            if (k + 1 in ends) if ends is not None else (off - start >= per):
                 self._close_bucket(start, off, members)
                 start, members = off, []
         if members:
@@ -164,6 +175,8 @@ class FlatGrads:
         import torch.distributed as dist
         b = self.buckets[i]
         b.mul_(1.0 / self._world)
+        if os.environ.get("MAMBA_B200_DEBUG_NO_COMM") == "1":   # measurement aid: everything but the collective
+            return
         dist.all_reduce(b, op=dist.ReduceOp.SUM, group=self._group)
 
     def allreduce_mean(self, world_size, group=None):
@@ -194,6 +207,21 @@ class FlatGrads:
                 self._reduce_bucket(i)
 
         self._hooks = [p.register_post_accumulate_grad_hook(hook) for p in self.params]
+
+    def launch_bucket(self, i, world_size, group=None):
+        """All-reduce bucket i NOW, from the calling thread: on CUDA on a side stream forked from the current one
+        (so that it runs under whatever the current stream does next), on CPU inline.  `finish()` joins."""
+        self._world, self._group = world_size, group
+        if world_size <= 1:
+            return
+        if not self.flat.is_cuda:
+            self._reduce_bucket(i)
+            return
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.flat.device)
+        self._side.wait_stream(torch.cuda.current_stream(self.flat.device))
+        with torch.cuda.stream(self._side):
+            self._reduce_bucket(i)
 
     def finish(self):
         """Join the side stream (after backward, before the optimizer reads the gradients)."""
@@ -226,7 +254,7 @@ class Trainer:
     # the default is the plain post-backward exchange (92-97 % weak-scaling efficiency at 8 GPUs as measured).
     def __init__(self, model, lr=None, autocast_dtype=torch.bfloat16, world_size=1, process_group=None,
                  batch_size=None, block_len=None, use_graph=True, bucket_mb=64, overlap_allreduce=False,
-                 async_wgrad=None):
+                 async_wgrad=None, stages=None):
         self.model = model
         self.device = next(model.parameters()).device
         self.autocast_dtype = autocast_dtype
@@ -238,13 +266,24 @@ class Trainer:
         self.trg = torch.zeros(B, T, dtype=torch.long, device=self.device)
         self.meta = torch.zeros(B, cc.N_META, dtype=torch.long, device=self.device)
         self.loss = torch.zeros((), device=self.device)
+        # Staged backward (world_size > 1, layout P): the layer stack is cut into `stages` groups; the backward runs
+        # group by group from the top and each group's gradient bucket is all-reduced on a side stream while the
+        # groups below it are still being differentiated — DDP's overlap (train_parallel.py:151), issued from the
+        # capturing thread so that it can live inside the CUDA graph.  stages = 1: one exchange after the backward.
+        if stages is None:
+            stages = int(os.environ.get("MAMBA_B200_STAGES", "5"))
+        self._stage_groups = None
+        if world_size > 1 and stages > 1 and getattr(model, "layout", None) == "P" and len(model.layers) >= stages:
+            layers = list(model.layers)
+            per = -(-len(layers) // stages)
+            self._stage_groups = [layers[i:i + per] for i in range(0, len(layers), per)]
         self._flatten_grads(bucket_mb)
         # weight-gradient GEMMs of the mixer's linear layers on a side stream (models.mamba.AsyncWgrad): needs
         # autocast (the fp32-output GEMM path) and gradient buffers that exist before backward
-        # (default: on for single-GPU training; measured +1 % — cuBLAS's 2-CTA-cluster GEMMs find few free TPCs
-        # next to the scans — and not yet exercised together with the NCCL exchange, so off for world_size > 1)
+        # (measured: +1 % on one GPU — cuBLAS's 2-CTA-cluster GEMMs find few free TPCs next to the scans — and +2 % at
+        # two GPUs, where it also saves the accumulate pass into the flat gradient buffer)
         if async_wgrad is None:
-            async_wgrad = os.environ.get("MAMBA_B200_ASYNC_WGRAD", "1" if world_size == 1 else "0") == "1"
+            async_wgrad = os.environ.get("MAMBA_B200_ASYNC_WGRAD", "1") == "1"
         self.async_wgrad = bool(async_wgrad) and self.device.type == "cuda" and autocast_dtype is not None
         self._wgrad_params = []
         if self.async_wgrad:
@@ -269,7 +308,21 @@ class Trainer:
     def _flatten_grads(self, bucket_mb):
         # one rank: autograd writes each gradient straight into a fresh buffer (no accumulate-add per parameter);
         # several ranks: gradients live in one flat buffer so that the exchange is a few large all-reduces
-        self.grads = FlatGrads(self.model.parameters(), bucket_mb) if self.world_size > 1 else None
+        if self.world_size <= 1:
+            self.grads = None
+        elif self._stage_groups is None:
+            self.grads = FlatGrads(self.model.parameters(), bucket_mb)
+        else:
+            # bucket i = parameters of layer group i; everything outside the layer stack that receives its last
+            # gradient contribution at the very end of the backward (embeddings, the tied head) joins group 0, the
+            # final norm joins the last group (its gradient is the first one to exist)
+            m = self.model
+            groups = [[p for layer in g for p in layer.parameters()] for g in self._stage_groups]
+            seen = {id(p) for g in groups for p in g}
+            groups[-1] = groups[-1] + [p for p in m.norm_f.parameters() if id(p) not in seen]
+            seen |= {id(p) for p in m.norm_f.parameters()}
+            groups[0] = groups[0] + [p for p in m.parameters() if id(p) not in seen]
+            self.grads = FlatGrads(None, bucket_mb, groups=groups)
 
     def _allreduce(self):
         if self.grads is None:
@@ -279,7 +332,43 @@ class Trainer:
         else:
             self.grads.allreduce_mean(self.world_size, self.pg)
 
+    def _join_wgrad(self):
+        if self.async_wgrad:
+            from .models.mamba.mamba import AsyncWgrad
+            AsyncWgrad.join()
+
+    def _step_body_staged(self):
+        m, groups = self.model, self._stage_groups
+        cuts = []
+        with torch.autocast(self.device.type, dtype=self.autocast_dtype, enabled=self.autocast_dtype is not None):
+            resid, hidden = m._embed(self.src, self.meta), None
+            for gi, group in enumerate(groups):
+                if gi > 0:  # cut the autograd graph below this group
+                    rd, hd = resid.detach().requires_grad_(True), hidden.detach().requires_grad_(True)
+                    cuts.append((resid, hidden, rd, hd))
+                    resid, hidden = rd, hd
+                for layer in group:
+                    normed, resid = layer.norm(hidden, resid)
+                    hidden = layer.mixer(normed)
+            normed, _ = m.norm_f(hidden, resid)
+            output = m._head(normed[:, self.meta.shape[-1]:])
+        loss = loss_fn(self.src, self.trg, output)
+        self.grads.zero()
+        loss.backward()
+        self._join_wgrad()   # side-stream weight gradients of this stage must be in the bucket before it is sent
+        self.grads.launch_bucket(len(groups) - 1, self.world_size, self.pg)
+        for gi in range(len(cuts) - 1, -1, -1):
+            r, h, rd, hd = cuts[gi]
+            torch.autograd.backward([r, h], [rd.grad, hd.grad])
+            self._join_wgrad()
+            self.grads.launch_bucket(gi, self.world_size, self.pg)
+        self.grads.finish()
+        self.optimizer.step()
+        self.loss.copy_(loss.detach())
+
     def _step_body(self):
+        if self._stage_groups is not None:
+            return self._step_body_staged()
         with torch.autocast("cuda", dtype=self.autocast_dtype, enabled=self.autocast_dtype is not None):
             output = self.model(self.src, self.meta)
         loss = loss_fn(self.src, self.trg, output)
@@ -291,9 +380,7 @@ class Trainer:
         else:
             self.grads.zero()
         loss.backward()
-        if self.async_wgrad:
-            from .models.mamba.mamba import AsyncWgrad
-            AsyncWgrad.join()
+        self._join_wgrad()
         self._allreduce()
         self.optimizer.step()
         self.loss.copy_(loss.detach())

@@ -84,3 +84,99 @@ def test_shard_rows_partitions_exactly():
             assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
             sizes = [hi - lo for lo, hi in parts]
             assert max(sizes) - min(sizes) <= 1
+
+
+class _FakeNorm(torch.nn.Module):
+    """Stand-in for models.mamba.RMSNorm's fused form: forward(x, residual) -> (norm(x + residual), x + residual)."""
+
+    def __init__(self, d):
+        super().__init__()
+        self.weight = torch.nn.Parameter(torch.ones(d))
+
+    def forward(self, x, residual):
+        r = residual if x is None else x + residual
+        return r * torch.rsqrt(r.square().mean(-1, keepdim=True) + 1e-5) * self.weight, r
+
+
+class _FakeLayer(torch.nn.Module):
+    def __init__(self, d):
+        super().__init__()
+        self.norm = _FakeNorm(d)
+        self.mixer = torch.nn.Sequential(torch.nn.Linear(d, d), torch.nn.Tanh())
+
+
+class _FakeMamba(torch.nn.Module):
+    """Layout-P skeleton (embedding tied to lm_head, pre-norm residual layers, norm_f) in plain torch: what Trainer's
+    staged backward walks, without the CUDA-only mixer."""
+    layout = "P"
+
+    def __init__(self, d=8, n_layers=4):
+        super().__init__()
+        from mamba_b200.configs import common as cc
+        self.embedding = torch.nn.Embedding(cc.vocab_size, d)
+        self.metadata_embedding = torch.nn.Embedding(cc.metadata_vocab_size, d)
+        self.layers = torch.nn.ModuleList(_FakeLayer(d) for _ in range(n_layers))
+        self.norm_f = _FakeNorm(d)
+        self.lm_head = torch.nn.Linear(d, cc.vocab_size, bias=False)
+        self.lm_head.weight = self.embedding.weight
+
+    def _embed(self, tokens, meta):
+        return torch.cat((self.metadata_embedding(meta), self.embedding(tokens)), dim=-2)
+
+    def _head(self, x):
+        return self.lm_head(x)
+
+    def forward(self, tokens, meta):
+        resid, hidden = self._embed(tokens, meta), None
+        for layer in self.layers:
+            normed, resid = layer.norm(hidden, resid)
+            hidden = layer.mixer(normed)
+        normed, _ = self.norm_f(hidden, resid)
+        return self._head(normed[:, meta.shape[-1]:])
+
+
+def _staged_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from mamba_b200 import synthetic, train
+        train.loss_fn = train.loss_fn_torch          # the fused loss is CUDA-only; same function in torch ops
+        out = []
+        for stages in (1, 2, 4):
+            torch.manual_seed(0)
+            model = _FakeMamba()
+            tr = train.Trainer(model, lr=1e-2, autocast_dtype=None, world_size=world, batch_size=2, block_len=12,
+                               use_graph=False, stages=stages)
+            assert (tr._stage_groups is None) == (stages == 1)
+            if stages > 1:
+                assert len(tr.grads.buckets) == stages
+                assert all(p.grad is not None for p in model.parameters())
+            losses = []
+            for i in range(3):
+                src, trg, meta = synthetic.batch(2, 12, seed=50 + 10 * i + rank)
+                losses.append(float(tr.step(src, trg, meta)))
+            out.append((losses, torch.cat([p.detach().flatten() for p in model.parameters()]).numpy()))  # by value
+        q.put((rank, out))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_staged_backward_with_per_stage_allreduce_equals_single_exchange():
+    """Trainer's staged backward (graph cut into layer groups, bucket i all-reduced as soon as group i's gradients
+    exist) trains exactly like one exchange after a plain backward, and every rank ends with the same parameters."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_staged_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=300) for _ in range(world)), key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank_out in res:
+        (l1, p1), (l2, p2), (l4, p4) = rank_out[1]
+        assert l1 == l2 == l4, (l1, l2, l4)
+        assert (p1 == p2).all() and (p1 == p4).all()
+    assert (res[0][1][0][1] == res[1][1][0][1]).all()   # ranks agree
