@@ -174,10 +174,13 @@ class FlatGrads:
     def _reduce_bucket(self, i):
         import torch.distributed as dist
         b = self.buckets[i]
-        b.mul_(1.0 / self._world)
         if os.environ.get("MAMBA_B200_DEBUG_NO_COMM") == "1":   # measurement aid: everything but the collective
             return
-        dist.all_reduce(b, op=dist.ReduceOp.SUM, group=self._group)
+        if b.is_cuda and dist.get_backend(self._group) == "nccl":
+            dist.all_reduce(b, op=dist.ReduceOp.AVG, group=self._group)   # the mean inside the collective: no pre-scale pass
+        else:
+            b.mul_(1.0 / self._world)
+            dist.all_reduce(b, op=dist.ReduceOp.SUM, group=self._group)
 
     def allreduce_mean(self, world_size, group=None):
         """Exchange every bucket now (no overlap)."""
