@@ -43,21 +43,33 @@ __global__ void __launch_bounds__(kGemvThreads) gemv_kernel(const GemvParams p) 
   extern __shared__ __align__(16) float xs[];  // [BT][K]
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int K4 = p.K >> 2;
-  {  // stage the activation rows as fp32 (128-bit where the rows allow it); rows >= B are zero
+  {  // stage the activation rows as fp32 (128-bit where the rows allow it); rows >= B are zero.  All of a thread's
+     // loads are issued before its first store: the copy is a handful of dependent L2 round trips otherwise, and
+     // at 10-16 rows that latency, not the weight stream, was the whole kernel.
     const bool vec = (reinterpret_cast<uintptr_t>(p.x) % (4 * sizeof(TX)) == 0) && (p.x_bs % 4 == 0);
-    for (int b = 0; b < BT; ++b) {
-      const TX* xr = static_cast<const TX*>(p.x) + (int64_t)b * p.x_bs;
-      float* dst = xs + b * p.K;
-      if (b >= p.B) {
-        for (int k4 = tid; k4 < K4; k4 += nthr) *reinterpret_cast<float4*>(dst + 4 * k4) = make_float4(0.f, 0.f, 0.f, 0.f);
-      } else if (vec) {
-        for (int k4 = tid; k4 < K4; k4 += nthr) {
-          float v[4];
-          V4<TX>::ld(xr + 4 * k4, v);
-          *reinterpret_cast<float4*>(dst + 4 * k4) = make_float4(v[0], v[1], v[2], v[3]);
+    if (vec) {
+      constexpr int U = 16;
+      const int total4 = BT * K4;
+      for (int base = tid; base < total4; base += nthr * U) {
+        float v[U][4];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int i = base + u * nthr;
+          const int b = i / K4, k4 = i - b * K4;
+          v[u][0] = v[u][1] = v[u][2] = v[u][3] = 0.f;
+          if (i < total4 && b < p.B) V4<TX>::ld(static_cast<const TX*>(p.x) + (int64_t)b * p.x_bs + 4 * k4, v[u]);
         }
-      } else {
-        for (int k = tid; k < p.K; k += nthr) dst[k] = IO<TX>::ld(xr + k);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int i = base + u * nthr;
+          if (i < total4) *reinterpret_cast<float4*>(xs + 4 * i) = make_float4(v[u][0], v[u][1], v[u][2], v[u][3]);
+        }
+      }
+    } else {
+      for (int b = 0; b < BT; ++b) {
+        const TX* xr = static_cast<const TX*>(p.x) + (int64_t)b * p.x_bs;
+        float* dst = xs + b * p.K;
+        for (int k = tid; k < p.K; k += nthr) dst[k] = b < p.B ? IO<TX>::ld(xr + k) : 0.f;
       }
     }
   }
@@ -75,7 +87,9 @@ __global__ void __launch_bounds__(kGemvThreads) gemv_kernel(const GemvParams p) 
     const TW* wrow[ROWS];
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) wrow[r] = static_cast<const TW*>(p.w) + (int64_t)min(n0 + r, p.N - 1) * p.K;
-#pragma unroll 4
+    // weight loads of 16 (one row per warp) or 4 (four rows) steps in flight per lane
+    constexpr int kUnrollK = ROWS == 1 ? 16 : 4;
+#pragma unroll kUnrollK
     for (int k4 = gl; k4 < K4; k4 += GW) {
       float2 w01[ROWS], w23[ROWS];
 #pragma unroll
