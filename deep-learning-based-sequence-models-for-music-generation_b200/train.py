@@ -160,6 +160,7 @@ class FlatGrads:
             self._close_bucket(start, off, members)
         self._pending = [0] * len(self.buckets)
         self._hooks, self._side, self._world, self._group = [], None, 1, None
+        self._done = {}
 
     def _close_bucket(self, start, end, members):
         idx = len(self.buckets)
@@ -225,6 +226,16 @@ class FlatGrads:
         self._side.wait_stream(torch.cuda.current_stream(self.flat.device))
         with torch.cuda.stream(self._side):
             self._reduce_bucket(i)
+            ev = torch.cuda.Event()
+            ev.record(self._side)
+            self._done[i] = ev
+
+    def wait_bucket(self, i):
+        """Make the current stream wait for bucket i's exchange only (the optimizer of that bucket's parameters can
+        then run while later buckets are still in flight)."""
+        ev = self._done.pop(i, None)
+        if ev is not None:
+            torch.cuda.current_stream(self.flat.device).wait_event(ev)
 
     def finish(self):
         """Join the side stream (after backward, before the optimizer reads the gradients)."""
@@ -305,6 +316,13 @@ class Trainer:
             self.grads.overlap_with_backward(world_size, process_group)
         lr = cc.config.values.learning_rate if lr is None else lr
         self.optimizer = torch.optim.Adam(model.parameters(), lr=lr, capturable=use_graph, fused=True)  # train.py:146
+        # staged exchange: the same Adam, one instance per gradient bucket, so that bucket k's parameters are updated
+        # as soon as ITS all-reduce is done — the update of the upper layers hides the exchange of the last bucket
+        self._stage_optimizers = None
+        if self._stage_groups is not None and self.device.type == "cuda":
+            per_bucket = [[p for p in self.grads.params if self.grads._bucket_of[id(p)] == i]
+                          for i in range(len(self.grads.buckets))]
+            self._stage_optimizers = [torch.optim.Adam(ps, lr=lr, capturable=use_graph, fused=True) for ps in per_bucket]
         self.use_graph = use_graph
         self.graph = None
 
@@ -365,8 +383,14 @@ class Trainer:
             torch.autograd.backward([r, h], [rd.grad, hd.grad])
             self._join_wgrad()
             self.grads.launch_bucket(gi, self.world_size, self.pg)
-        self.grads.finish()
-        self.optimizer.step()
+        if self._stage_optimizers is None:
+            self.grads.finish()
+            self.optimizer.step()
+        else:
+            for gi in range(len(groups) - 1, -1, -1):   # in launch order: top bucket first
+                self.grads.wait_bucket(gi)
+                self._stage_optimizers[gi].step()
+            self.grads.finish()
         self.loss.copy_(loss.detach())
 
     def _step_body(self):
@@ -406,10 +430,11 @@ class Trainer:
         with torch.no_grad():
             for p, q in zip(self.model.parameters(), saved):
                 p.copy_(q)
-            for st in self.optimizer.state.values():   # exp_avg, exp_avg_sq and the device-side step counter
-                for v in st.values():
-                    if torch.is_tensor(v):
-                        v.zero_()
+            for opt in [self.optimizer] + (self._stage_optimizers or []):
+                for st in opt.state.values():   # exp_avg, exp_avg_sq and the device-side step counter
+                    for v in st.values():
+                        if torch.is_tensor(v):
+                            v.zero_()
         torch.cuda.synchronize(self.device)
 
     def step(self, src, trg, meta):
