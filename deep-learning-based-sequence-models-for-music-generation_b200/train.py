@@ -286,11 +286,21 @@ class Trainer:
         # capturing thread so that it can live inside the CUDA graph.  stages = 1: one exchange after the backward.
         if stages is None:
             stages = int(os.environ.get("MAMBA_B200_STAGES", "5"))
-        self._stage_groups = None
-        if world_size > 1 and stages > 1 and getattr(model, "layout", None) == "P" and len(model.layers) >= stages:
+        self._stage_groups = self._stage_params = None
+        staged_ok = world_size > 1 or self.device.type == "cuda"   # one rank on CPU: nothing to overlap
+        if staged_ok and stages > 1 and getattr(model, "layout", None) == "P" and len(model.layers) >= stages:
             layers = list(model.layers)
             per = -(-len(layers) // stages)
             self._stage_groups = [layers[i:i + per] for i in range(0, len(layers), per)]
+            # parameters of stage i; everything outside the layer stack that receives its last gradient contribution
+            # at the very end of the backward (embeddings, the tied head) joins stage 0, the final norm joins the
+            # last stage (its gradient is the first one to exist)
+            groups = [[p for layer in g for p in layer.parameters()] for g in self._stage_groups]
+            seen = {id(p) for g in groups for p in g}
+            groups[-1] = groups[-1] + [p for p in model.norm_f.parameters() if id(p) not in seen]
+            seen |= {id(p) for p in model.norm_f.parameters()}
+            groups[0] = groups[0] + [p for p in model.parameters() if id(p) not in seen]
+            self._stage_params = [[p for p in g if p.requires_grad] for g in groups]
         self._flatten_grads(bucket_mb)
         # weight-gradient GEMMs of the mixer's linear layers on a side stream (models.mamba.AsyncWgrad): needs
         # autocast (the fp32-output GEMM path) and gradient buffers that exist before backward
@@ -318,11 +328,15 @@ class Trainer:
         self.optimizer = torch.optim.Adam(model.parameters(), lr=lr, capturable=use_graph, fused=True)  # train.py:146
         # staged exchange: the same Adam, one instance per gradient bucket, so that bucket k's parameters are updated
         # as soon as ITS all-reduce is done — the update of the upper layers hides the exchange of the last bucket
-        self._stage_optimizers = None
+        # On one GPU the same structure overlaps the (memory-bound) parameter update of the upper stages with the
+        # (compute-bound) backward of the lower ones.
+        self._stage_optimizers, self._side = None, None
         if self._stage_groups is not None and self.device.type == "cuda":
-            per_bucket = [[p for p in self.grads.params if self.grads._bucket_of[id(p)] == i]
-                          for i in range(len(self.grads.buckets))]
-            self._stage_optimizers = [torch.optim.Adam(ps, lr=lr, capturable=use_graph, fused=True) for ps in per_bucket]
+            self._stage_optimizers = [torch.optim.Adam(ps, lr=lr, capturable=use_graph, fused=True)
+                                      for ps in self._stage_params]
+            self._side = torch.cuda.Stream(device=self.device)
+            if self.grads is not None:
+                self.grads._side = self._side
         self.use_graph = use_graph
         self.graph = None
 
@@ -334,16 +348,7 @@ class Trainer:
         elif self._stage_groups is None:
             self.grads = FlatGrads(self.model.parameters(), bucket_mb)
         else:
-            # bucket i = parameters of layer group i; everything outside the layer stack that receives its last
-            # gradient contribution at the very end of the backward (embeddings, the tied head) joins group 0, the
-            # final norm joins the last group (its gradient is the first one to exist)
-            m = self.model
-            groups = [[p for layer in g for p in layer.parameters()] for g in self._stage_groups]
-            seen = {id(p) for g in groups for p in g}
-            groups[-1] = groups[-1] + [p for p in m.norm_f.parameters() if id(p) not in seen]
-            seen |= {id(p) for p in m.norm_f.parameters()}
-            groups[0] = groups[0] + [p for p in m.parameters() if id(p) not in seen]
-            self.grads = FlatGrads(None, bucket_mb, groups=groups)
+            self.grads = FlatGrads(None, bucket_mb, groups=self._stage_params)   # bucket i = parameters of stage i
 
     def _allreduce(self):
         if self.grads is None:
@@ -374,31 +379,37 @@ class Trainer:
             normed, _ = m.norm_f(hidden, resid)
             output = m._head(normed[:, self.meta.shape[-1]:])
         loss = loss_fn(self.src, self.trg, output)
-        self.grads.zero()
+        self._zero_grads()
         loss.backward()
-        self._join_wgrad()   # side-stream weight gradients of this stage must be in the bucket before it is sent
-        self.grads.launch_bucket(len(groups) - 1, self.world_size, self.pg)
+        self._finish_stage(len(groups) - 1)
         for gi in range(len(cuts) - 1, -1, -1):
             r, h, rd, hd = cuts[gi]
             torch.autograd.backward([r, h], [rd.grad, hd.grad])
-            self._join_wgrad()
-            self.grads.launch_bucket(gi, self.world_size, self.pg)
+            self._finish_stage(gi)
         if self._stage_optimizers is None:
             self.grads.finish()
             self.optimizer.step()
         else:
-            for gi in range(len(groups) - 1, -1, -1):   # in launch order: top bucket first
-                self.grads.wait_bucket(gi)
-                self._stage_optimizers[gi].step()
-            self.grads.finish()
+            torch.cuda.current_stream(self.device).wait_stream(self._side)
         self.loss.copy_(loss.detach())
 
-    def _step_body(self):
-        if self._stage_groups is not None:
-            return self._step_body_staged()
-        with torch.autocast("cuda", dtype=self.autocast_dtype, enabled=self.autocast_dtype is not None):
-            output = self.model(self.src, self.meta)
-        loss = loss_fn(self.src, self.trg, output)
+    def _finish_stage(self, gi):
+        """Stage gi's gradients are complete on the current stream: exchange them (world_size > 1) and update the
+        stage's parameters, both on the side stream, while the current stream goes on with the stages below."""
+        if self._stage_optimizers is None:   # CPU (gloo tests): exchange inline, one optimizer step at the end
+            self.grads.launch_bucket(gi, self.world_size, self.pg)
+            return
+        self._side.wait_stream(torch.cuda.current_stream(self.device))
+        if self.async_wgrad:   # the stage's side-stream weight gradients must be in place too; the main stream need
+            from .models.mamba.mamba import AsyncWgrad   # not wait for them
+            self._side.wait_stream(AsyncWgrad.stream)
+        with torch.cuda.stream(self._side):
+            if self.grads is not None and self.world_size > 1:
+                self.grads._world, self.grads._group = self.world_size, self.pg
+                self.grads._reduce_bucket(gi)
+            self._stage_optimizers[gi].step()
+
+    def _zero_grads(self):
         if self.grads is None:
             keep = [p.grad for p in self._wgrad_params]       # overwritten (not accumulated) by the side-stream GEMMs
             self.optimizer.zero_grad(set_to_none=True)
@@ -406,6 +417,14 @@ class Trainer:
                 p.grad = g
         else:
             self.grads.zero()
+
+    def _step_body(self):
+        if self._stage_groups is not None:
+            return self._step_body_staged()
+        with torch.autocast("cuda", dtype=self.autocast_dtype, enabled=self.autocast_dtype is not None):
+            output = self.model(self.src, self.meta)
+        loss = loss_fn(self.src, self.trg, output)
+        self._zero_grads()
         loss.backward()
         self._join_wgrad()
         self._allreduce()

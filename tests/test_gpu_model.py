@@ -199,6 +199,32 @@ def test_trainer_graph_step_equals_eager_step():
 
 
 @pytest.mark.parametrize("use_graph", [False, True])
+@pytest.mark.parametrize("stages", [2, 4])
+def test_staged_backward_with_side_stream_adam_equals_plain_step(use_graph, stages):
+    """One GPU: the staged step (backward cut into layer groups, each group's Adam update on a side stream under
+    the backward of the groups below) trains bit-identically to backward-then-Adam."""
+    from mamba_b200 import synthetic, train
+    from mamba_b200.models.mamba import Mamba, ModelArgs
+    from mamba_b200.models.mamba.mamba import AsyncWgrad
+    torch.manual_seed(0)
+    a = Mamba(_args(ModelArgs, d_model=64, d_state=64, n_layer=4)).cuda()
+    b = Mamba(_args(ModelArgs, d_model=64, d_state=64, n_layer=4)).cuda()
+    b.load_state_dict(a.state_dict())
+    try:
+        ta = train.Trainer(a, lr=1e-3, batch_size=2, block_len=40, use_graph=use_graph, stages=1)
+        tb = train.Trainer(b, lr=1e-3, batch_size=2, block_len=40, use_graph=use_graph, stages=stages)
+        assert ta._stage_groups is None and len(tb._stage_groups) == stages and len(tb._stage_optimizers) == stages
+        for i in range(3):
+            batch = [t.cuda() for t in synthetic.batch(2, 40, seed=40 + i)]
+            la, lb = ta.step(*batch).item(), tb.step(*batch).item()
+            assert la == lb, (i, la, lb)
+    finally:
+        AsyncWgrad.disable()
+    for (n1, p1), (n2, p2) in zip(a.named_parameters(), b.named_parameters()):
+        assert torch.equal(p1, p2), f"param {n1} differs between the staged and the plain step"
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
 def test_side_stream_weight_gradients_equal_inline_ones(use_graph):
     """bf16-autocast training steps with the weight-gradient GEMMs on the side stream (AsyncWgrad, written straight
     into param.grad) and with them inline: same losses, same parameters after 3 Adam steps (same GEMMs, same
