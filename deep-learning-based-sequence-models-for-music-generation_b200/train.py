@@ -177,8 +177,10 @@ class FlatGrads:
         b = self.buckets[i]
         if os.environ.get("MAMBA_B200_DEBUG_NO_COMM") == "1":   # measurement aid: everything but the collective
             return
-        if b.is_cuda and dist.get_backend(self._group) == "nccl":
-            dist.all_reduce(b, op=dist.ReduceOp.AVG, group=self._group)   # the mean inside the collective: no pre-scale pass
+        if b.is_cuda and dist.get_backend(self._group) == "nccl" and os.environ.get("MAMBA_B200_NCCL_AVG", "0") == "1":
+            # the mean inside the collective saves the pre-scale pass, but ncclAvg measured SLOWER than pre-scale + sum
+            # at 8 GPUs (14.68 vs 14.31 ms/step: it leaves the in-switch NVLS reduction) — opt-in only
+            dist.all_reduce(b, op=dist.ReduceOp.AVG, group=self._group)
         else:
             b.mul_(1.0 / self._world)
             dist.all_reduce(b, op=dist.ReduceOp.SUM, group=self._group)

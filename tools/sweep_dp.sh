@@ -9,7 +9,5 @@ try:
     d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('N=$N $name', round(d['value']), round(d['ms_per_step'],3), d['loss'])
 except Exception as e: print('N=$N $name', 'FAILED', e)"
 }
-run default
-run ctas16 NCCL_MAX_CTAS=16
-run old MAMBA_B200_STAGES=1 MAMBA_B200_ASYNC_WGRAD=0
-run stages10 MAMBA_B200_STAGES=10
+run sum_prescale MAMBA_B200_NCCL_AVG=0
+run avg MAMBA_B200_NCCL_AVG=1
