@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Turn an `ncu --metrics gpu__time_duration.sum --csv` log of bench.py into the per-kernel launch list of ONE
-training step (kept under profiles/).  A step is delimited by the fused-Adam launches that end it.
+training step (kept under profiles/).  A step is the window between two launches of the loss-mean kernel (one per step).
 
     python tools/launch_list.py gpurun_out/launches.csv > profiles/rNN_bench_step_launches.txt
 """
@@ -25,10 +25,12 @@ def main():
     for r in csv.DictReader(lines):
         if r.get("Metric Name") == "gpu__time_duration.sum":
             rows.append((r["Kernel Name"], float(r["Metric Value"]) / 1e3))
-    ends = [i for i, (n, _) in enumerate(rows) if "multi_tensor_apply" in n and (i + 1 == len(rows) or "multi_tensor_apply" not in rows[i + 1][0])]
-    if len(ends) < 2:
-        raise SystemExit("fewer than two optimizer steps in the log")
-    step = rows[ends[-2] + 1:ends[-1] + 1]
+    # one launch of the loss-mean kernel per step (the staged step interleaves its per-stage Adam launches with the
+    # backward, so the optimizer is no delimiter): the window runs from one step's loss to the next one's
+    marks = [i for i, (n, _) in enumerate(rows) if "loss_mean_kernel" in n]
+    if len(marks) < 2:
+        raise SystemExit("fewer than two training steps in the log")
+    step = rows[marks[-2]:marks[-1]]
     agg = collections.OrderedDict()
     for n, us in step:
         k = short(n)
