@@ -8,7 +8,7 @@ HERE = Path(__file__).resolve().parent
 LIB_PATH = HERE / "libmamba_b200.so"
 
 MAMBA_F32, MAMBA_BF16 = 0, 1
-FLAG_HAS_Z, FLAG_DELTA_SOFTPLUS, FLAG_HAS_DELTA_BIAS, FLAG_HAS_D = 1, 2, 4, 8
+FLAG_HAS_Z, FLAG_DELTA_SOFTPLUS, FLAG_HAS_DELTA_BIAS, FLAG_HAS_D, FLAG_A_IS_LOG = 1, 2, 4, 8, 16
 
 EXPORTS = [
     "mamba_abi_version", "mamba_last_error", "mamba_launch_count",

@@ -50,6 +50,13 @@ __device__ __forceinline__ float silu_f(float x) { return x / (1.f + expf(-x)); 
 
 __device__ __forceinline__ void st_cs_f4(float* p, float4 v);
 
+// A[d, n] as the scans use it: the stored value, or -exp(stored) when the caller passes A_log (MAMBA_FLAG_A_IS_LOG;
+// reference: A = -torch.exp(self.A_log.float()), simple_mamba.pyc @L270)
+__device__ __forceinline__ float load_A(const float* A, int64_t i, int flags) {
+  const float v = A[i];
+  return (flags & MAMBA_FLAG_A_IS_LOG) ? -expf(v) : v;
+}
+
 // ---- fast transcendental helpers (MUFU ex2 / lg2 / rcp; relative error ~1e-7, far inside rtol 1e-4) ----------
 __device__ __forceinline__ float lg2_approx(float x) {
   float y;

@@ -95,7 +95,7 @@ __global__ void __launch_bounds__((NW + kBHelperWarps) * 32, 1) scan_bwd_kernel(
 #pragma unroll
     for (int j = 0; j < NPER; ++j) {
       const int n = n0 + j;
-      const float a = (d < p.D && n < p.N) ? p.A[(int64_t)d * p.N + n] * kLog2e : 0.f;
+      const float a = (d < p.D && n < p.N) ? load_A(p.A, (int64_t)d * p.N + n, p.flags) * kLog2e : 0.f;
       if (j & 1) A2[j / 2].y = a;
       else A2[j / 2].x = a;
     }
@@ -559,7 +559,8 @@ __global__ void scan_bwd_finalize_kernel(const ScanBwdParams p, int rows_per_blo
       const int n = (int)(i / p.D), d = (int)(i % p.D);
       float acc = 0.f;
       for (int b = 0; b < p.B; ++b) acc += p.ws_dA[(int64_t)b * DN + i];
-      p.dA[(int64_t)d * p.N + n] = acc;
+      // with A given as A_log: d/dA_log = dA * A, A = -exp(A_log)
+      p.dA[(int64_t)d * p.N + n] = (p.flags & MAMBA_FLAG_A_IS_LOG) ? acc * load_A(p.A, (int64_t)d * p.N + n, p.flags) : acc;
     }
     for (int64_t d = idx0; d < p.D; d += stride) {
       float sD = 0.f, sb = 0.f;

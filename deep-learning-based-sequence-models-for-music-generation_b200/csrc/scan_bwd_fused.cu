@@ -138,7 +138,7 @@ __global__ void __launch_bounds__((NW + kBHelperWarps) * 32, 1) scan_bwd_fused_k
     for (int ch = 0; ch < 2; ++ch)
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float a = d + ch < p.D ? p.A[(int64_t)(d + ch) * p.N + n0 + j] * kLog2e : 0.f;
+        const float a = d + ch < p.D ? load_A(p.A, (int64_t)(d + ch) * p.N + n0 + j, p.flags) * kLog2e : 0.f;
         if (j & 1) A2[ch][j / 2].y = a;
         else A2[ch][j / 2].x = a;
         dAacc[ch][j / 2] = dhc[ch][j / 2] = make_float2(0.f, 0.f);

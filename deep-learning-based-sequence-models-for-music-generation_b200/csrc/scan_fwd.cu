@@ -99,7 +99,7 @@ __global__ void __launch_bounds__((kMaxScanWarps + kHelperWarps) * 32) scan_fwd_
     for (int j = 0; j < NPER; ++j) {
       const int n = s * NPER + j;
       const bool ok = (d < p.D) && (n < p.N);
-      const float a = ok ? p.A[(int64_t)d * p.N + n] * kLog2e : 0.f;
+      const float a = ok ? load_A(p.A, (int64_t)d * p.N + n, p.flags) * kLog2e : 0.f;
       const float h0 = (ok && p.h_init) ? p.h_init[((int64_t)b * p.D + d) * p.N + n] : 0.f;
       if (j & 1) A2[j / 2].y = a, h[j / 2].y = h0;
       else A2[j / 2].x = a, h[j / 2].x = h0;

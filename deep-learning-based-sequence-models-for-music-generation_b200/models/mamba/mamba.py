@@ -185,12 +185,13 @@ class MambaBlock(nn.Module):  # simple_mamba @L184
         xz = _linear(x, self.in_proj.weight, self.in_proj.bias)           # @L230  [B, L, 2*d_inner]
         xs, res = xz.split([p.d_inner, p.d_inner], dim=-1)                # @L231  views, no copy
         xc = ops.causal_conv1d_silu_fn(xs, self.conv1d.weight, self.conv1d.bias)   # @L233-237 (one kernel)
-        A = -torch.exp(self.A_log.float())                                # @L270
         x_dbl = _linear(xc, self.x_proj.weight)                           # @L273
         dt_r, Bm, Cm = x_dbl.split([p.dt_rank, p.d_state, p.d_state], dim=-1)  # @L275 views
         dt_raw = _linear(dt_r, self.dt_proj.weight)                       # @L276: bias + softplus fused below
-        y = ops.selective_scan_fn(xc, dt_raw, A, Bm, Cm, self.D.float(), z=res,
-                                  delta_bias=self.dt_proj.bias.float(), delta_softplus=True)  # @L276-278, @L241
+        # A = -exp(A_log) (@L270) is formed inside the kernels; the gradient comes back w.r.t. A_log
+        y = ops.selective_scan_fn(xc, dt_raw, self.A_log, Bm, Cm, self.D.float(), z=res,
+                                  delta_bias=self.dt_proj.bias.float(), delta_softplus=True,
+                                  A_is_log=True)                          # @L270, @L276-278, @L241
         return _linear(y, self.out_proj.weight, self.out_proj.bias)       # @L243
 
     # ---- inference: full-sequence forward that also leaves the recurrent state behind ---------------

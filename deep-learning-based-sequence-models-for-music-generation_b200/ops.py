@@ -18,7 +18,7 @@ import os
 import torch
 
 from . import _lib
-from ._lib import (FLAG_DELTA_SOFTPLUS, FLAG_HAS_D, FLAG_HAS_DELTA_BIAS, FLAG_HAS_Z, MAMBA_BF16, MAMBA_F32, ConvArgs,
+from ._lib import (FLAG_A_IS_LOG, FLAG_DELTA_SOFTPLUS, FLAG_HAS_D, FLAG_HAS_DELTA_BIAS, FLAG_HAS_Z, MAMBA_BF16, MAMBA_F32, ConvArgs,
                    LinearStepArgs, LossArgs, NormArgs, ScanBwdArgs, ScanFwdArgs, StepArgs, check, lib)
 
 _DTYPES = {torch.float32: MAMBA_F32, torch.bfloat16: MAMBA_BF16}
@@ -84,7 +84,7 @@ def _call(name, a, dev):
 # selective scan
 # ------------------------------------------------------------------------------------------------
 def _scan_fwd_raw(u, delta, A, B, C, D, z, delta_bias, delta_softplus, ckpt, chunk, h_init=None, h_last=None,
-                  variant=0, y_pre=None, out=None):
+                  variant=0, y_pre=None, out=None, a_is_log=False):
     Bsz, L, Dm = u.shape
     N = A.shape[1]
     if out is None:
@@ -95,7 +95,8 @@ def _scan_fwd_raw(u, delta, A, B, C, D, z, delta_bias, delta_softplus, ckpt, chu
     a.batch, a.seqlen, a.dim, a.dstate = Bsz, L, Dm, N
     a.chunk = chunk
     a.flags = ((FLAG_HAS_Z if z is not None else 0) | (FLAG_DELTA_SOFTPLUS if delta_softplus else 0)
-               | (FLAG_HAS_DELTA_BIAS if delta_bias is not None else 0) | (FLAG_HAS_D if D is not None else 0))
+               | (FLAG_HAS_DELTA_BIAS if delta_bias is not None else 0) | (FLAG_HAS_D if D is not None else 0)
+               | (FLAG_A_IS_LOG if a_is_log else 0))
     a.variant = variant
     a.u, a.u_bs, a.u_ls = _p(u), u.stride(0), u.stride(1)
     a.delta, a.delta_bs, a.delta_ls = _p(delta), delta.stride(0), delta.stride(1)
@@ -118,7 +119,7 @@ def _scan_fwd_raw(u, delta, A, B, C, D, z, delta_bias, delta_softplus, ckpt, chu
 
 class SelectiveScanFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, u, delta, A, B, C, D, z, delta_bias, delta_softplus, chunk):
+    def forward(ctx, u, delta, A, B, C, D, z, delta_bias, delta_softplus, chunk, a_is_log=False):
         _require_cuda(u, delta, A, B, C, D, z, delta_bias)
         if u.dim() != 3 or delta.shape != u.shape:
             raise ValueError(f"selective_scan: u {tuple(u.shape)} and delta {tuple(delta.shape)} must be equal [B, L, D]")
@@ -139,9 +140,10 @@ class SelectiveScanFn(torch.autograd.Function):
         if need_grad and z is not None:
             y_pre = torch.empty(u.shape, dtype=u.dtype, device=u.device)  # pre-gate output, for dz
         out = _scan_fwd_raw(u, delta, A32, B, C, D32, z, b32, delta_softplus, ckpt, chunk, variant=SCAN_FWD_VARIANT,
-                            y_pre=y_pre)
+                            y_pre=y_pre, a_is_log=a_is_log)
         ctx.save_for_backward(u, delta, A32, B, C, D32, z, b32, ckpt, y_pre)
         ctx.delta_softplus = delta_softplus
+        ctx.a_is_log = a_is_log
         ctx.chunk = chunk
         ctx.in_dtypes = (A.dtype, None if D is None else D.dtype, None if delta_bias is None else delta_bias.dtype)
         return out
@@ -169,7 +171,8 @@ class SelectiveScanFn(torch.autograd.Function):
         a.batch, a.seqlen, a.dim, a.dstate = Bsz, L, Dm, N
         a.chunk = ctx.chunk
         a.flags = ((FLAG_HAS_Z if z is not None else 0) | (FLAG_DELTA_SOFTPLUS if ctx.delta_softplus else 0)
-                   | (FLAG_HAS_DELTA_BIAS if dbias is not None else 0) | (FLAG_HAS_D if D is not None else 0))
+                   | (FLAG_HAS_DELTA_BIAS if dbias is not None else 0) | (FLAG_HAS_D if D is not None else 0)
+                   | (FLAG_A_IS_LOG if ctx.a_is_log else 0))
         a.variant = SCAN_BWD_VARIANT
         a.u, a.u_bs, a.u_ls = _p(u), u.stride(0), u.stride(1)
         a.delta, a.delta_bs, a.delta_ls = _p(delta), delta.stride(0), delta.stride(1)
@@ -193,16 +196,19 @@ class SelectiveScanFn(torch.autograd.Function):
         _call("mamba_scan_bwd", a, dev)
         tA, tD, tb = ctx.in_dtypes
         return (du, ddelta, dA.to(tA), dB, dC, None if dD is None else dD.to(tD), dz,
-                None if ddb is None else ddb.to(tb), None, None)
+                None if ddb is None else ddb.to(tb), None, None, None)
 
 
 
 
-def selective_scan_fn(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus=False, chunk=None):
+def selective_scan_fn(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus=False, chunk=None,
+                      A_is_log=False):
     """Fused selective scan.  u, delta: [B, L, D]; A: [D, N]; B, C: [B, L, N]; D, delta_bias: [D];
-    z: [B, L, D].  Returns out [B, L, D] = (scan(u, delta, A, B, C) + D*u) * silu(z)."""
+    z: [B, L, D].  Returns out [B, L, D] = (scan(u, delta, A, B, C) + D*u) * silu(z).
+    A_is_log: `A` is the A_log parameter; the kernels form A = -exp(A_log) (simple_mamba @L270) themselves and the
+    gradient comes back w.r.t. A_log (saves five elementwise launches per layer and step)."""
     return SelectiveScanFn.apply(u, delta, A, B, C, D, z, delta_bias, bool(delta_softplus),
-                                 SCAN_CHUNK if chunk is None else int(chunk))
+                                 SCAN_CHUNK if chunk is None else int(chunk), bool(A_is_log))
 
 
 def selective_scan_prefill(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus=False, h_init=None):

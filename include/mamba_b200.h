@@ -49,7 +49,9 @@ enum {
   MAMBA_FLAG_HAS_Z = 1,          /* out = y * silu(z)             (simple_mamba.pyc @L241)  */
   MAMBA_FLAG_DELTA_SOFTPLUS = 2, /* delta = softplus(delta_raw)   (simple_mamba.pyc @L276)  */
   MAMBA_FLAG_HAS_DELTA_BIAS = 4, /* delta_raw += delta_bias[d]    (dt_proj bias, @L276)     */
-  MAMBA_FLAG_HAS_D = 8           /* y += u * D                    (simple_mamba.pyc @L331)  */
+  MAMBA_FLAG_HAS_D = 8,          /* y += u * D                    (simple_mamba.pyc @L331)  */
+  MAMBA_FLAG_A_IS_LOG = 16       /* `A` holds A_log: the kernels use A = -exp(A_log) (@L270) and the backward
+                                    returns dA w.r.t. A_log (= dA * A)                                      */
 };
 
 /* ------------------------------------------------------------------------------------------

@@ -536,3 +536,31 @@ def test_scan_backward_writes_stay_inside_their_buffers(shape, dtype, variant, m
     rtol, floor = (RTOL32, 1e-5) if dtype == torch.float32 else (RTOL16, FLOOR16)
     for k in c:
         assert_close(g[k].grad, c[k].grad, rtol, floor, what=f"guarded scan bwd d{k} {shape}", atol_abs=1e-6 if k == "A" else 0.0)
+
+
+@pytest.mark.parametrize("shape,dtype", [((2, 70, 64, 16), torch.float32), ((1, 100, 96, 64), torch.float32),
+                                         ((2, 100, 72, 64), torch.bfloat16)])
+def test_scan_with_A_given_as_A_log(shape, dtype):
+    """MAMBA_FLAG_A_IS_LOG: the kernels form A = -exp(A_log) (simple_mamba @L270) themselves and return the gradient
+    w.r.t. A_log; same outputs and gradients as passing A and letting autograd chain through -exp."""
+    from mamba_b200 import ops
+    B, L, D, N = shape
+    t = scan_inputs(B, L, D, N, seed=17, dtype=dtype)
+    A_log = torch.log(-t["A"])
+    dout = torch.randn(B, L, D, generator=torch.Generator().manual_seed(8)).to(dtype)
+    c = _leafs(t, "cpu")
+    c_Alog = A_log.clone().requires_grad_(True)
+    cc_ = dict(c)
+    cc_["A"] = -torch.exp(c_Alog)
+    ref = _oracle_scan(cc_)
+    ref.backward(dout.float())
+    g = _leafs(t, "cuda")
+    g_Alog = A_log.clone().cuda().requires_grad_(True)
+    out = ops.selective_scan_fn(g["u"], g["delta_raw"], g_Alog, g["B"], g["C"], g["D"], z=g["z"], delta_bias=g["bias"],
+                                delta_softplus=True, A_is_log=True)
+    out.backward(dout.cuda())
+    rtol, floor = (RTOL32, 1e-5) if dtype == torch.float32 else (RTOL16, FLOOR16)
+    assert_close(out, ref, rtol, floor, what=f"scan fwd (A_log) {shape}")
+    assert_close(g_Alog.grad, c_Alog.grad, rtol, floor, what=f"scan bwd dA_log {shape}", atol_abs=1e-6)
+    for k in ("u", "delta_raw", "B", "C", "D", "z", "bias"):
+        assert_close(g[k].grad, c[k].grad, rtol, floor, what=f"scan bwd (A_log) d{k} {shape}")
