@@ -97,7 +97,8 @@ class _LinearFn(torch.autograd.Function):
     instead of as a bf16 product followed by a separate widening pass over every weight matrix."""
 
     @staticmethod
-    def forward(ctx, x, w, dt):
+    def forward(ctx, x, w, dt, plan=None):
+        ctx.plan = plan
         wc = w.to(dt)
         x2 = x.reshape(-1, x.shape[-1])
         if x2.dtype != dt:
@@ -117,9 +118,17 @@ class _LinearFn(torch.autograd.Function):
             g2 = g2.to(wc.dtype)
         dx = dw = None
         if ctx.needs_input_grad[0]:
-            dx = torch.mm(g2, wc).view(xshape)
-            if dx.dtype != xdt:
-                dx = dx.to(xdt)
+            plan = ctx.plan
+            if plan is not None and plan.xdbl_shape is not None and xdt == wc.dtype:
+                # dt_proj: d(dt_r) is the first slice of d(x_dbl); the GEMM writes it in place (ops.MixerGradPlan)
+                buf = plan.buffer("xdbl", plan.xdbl_shape, xdt, g2.device)
+                R = xshape[-1]
+                torch.mm(g2, wc, out=buf.view(-1, buf.shape[-1])[:, :R])
+                dx = buf[..., :R]
+            else:
+                dx = torch.mm(g2, wc).view(xshape)
+                if dx.dtype != xdt:
+                    dx = dx.to(xdt)
         if ctx.needs_input_grad[1]:
             side, p = AsyncWgrad.stream, ctx.param
             if (side is not None and p is not None and p.grad is not None and p.grad.dtype == wdt
@@ -132,13 +141,13 @@ class _LinearFn(torch.autograd.Function):
                 g2.record_stream(side), x2.record_stream(side)
             else:
                 dw = torch.mm(g2.t(), x2) if wdt == g2.dtype else torch.mm(g2.t(), x2, out_dtype=wdt)
-        return dx, dw, None
+        return dx, dw, None, None
 
 
-def _linear(x, weight, bias=None):
+def _linear(x, weight, bias=None, plan=None):
     """F.linear; on CUDA under autocast (and without a bias) through _LinearFn."""
     if bias is None and x.is_cuda and torch.is_autocast_enabled("cuda"):
-        return _LinearFn.apply(x, weight, torch.get_autocast_dtype("cuda"))
+        return _LinearFn.apply(x, weight, torch.get_autocast_dtype("cuda"), plan)
     return F.linear(x, weight, bias)
 
 
@@ -183,15 +192,20 @@ class MambaBlock(nn.Module):  # simple_mamba @L184
     def forward(self, x):
         p = self.params
         xz = _linear(x, self.in_proj.weight, self.in_proj.bias)           # @L230  [B, L, 2*d_inner]
-        xs, res = xz.split([p.d_inner, p.d_inner], dim=-1)                # @L231  views, no copy
-        xc = ops.causal_conv1d_silu_fn(xs, self.conv1d.weight, self.conv1d.bias)   # @L233-237 (one kernel)
+        # training on CUDA under autocast: the gradients of the split() views are written in place into one buffer
+        # per split instead of being concatenated (ops.MixerGradPlan)
+        plan = None
+        if torch.is_grad_enabled() and xz.requires_grad and xz.is_cuda and torch.is_autocast_enabled("cuda"):
+            plan = ops.MixerGradPlan(xz.shape, xz.shape[:-1] + (p.dt_rank + 2 * p.d_state,))
+        xs, res = ops.split_fn(xz, [p.d_inner, p.d_inner], plan, "xz")    # @L231  views, no copy
+        xc = ops.causal_conv1d_silu_fn(xs, self.conv1d.weight, self.conv1d.bias, plan=plan)   # @L233-237 (one kernel)
         x_dbl = _linear(xc, self.x_proj.weight)                           # @L273
-        dt_r, Bm, Cm = x_dbl.split([p.dt_rank, p.d_state, p.d_state], dim=-1)  # @L275 views
-        dt_raw = _linear(dt_r, self.dt_proj.weight)                       # @L276: bias + softplus fused below
+        dt_r, Bm, Cm = ops.split_fn(x_dbl, [p.dt_rank, p.d_state, p.d_state], plan, "xdbl")  # @L275 views
+        dt_raw = _linear(dt_r, self.dt_proj.weight, plan=plan)            # @L276: bias + softplus fused below
         # A = -exp(A_log) (@L270) is formed inside the kernels; the gradient comes back w.r.t. A_log
         y = ops.selective_scan_fn(xc, dt_raw, self.A_log, Bm, Cm, self.D.float(), z=res,
                                   delta_bias=self.dt_proj.bias.float(), delta_softplus=True,
-                                  A_is_log=True)                          # @L270, @L276-278, @L241
+                                  A_is_log=True, plan=plan)               # @L270, @L276-278, @L241
         return _linear(y, self.out_proj.weight, self.out_proj.bias)       # @L243
 
     # ---- inference: full-sequence forward that also leaves the recurrent state behind ---------------

@@ -81,6 +81,67 @@ def _call(name, a, dev):
 
 
 # ------------------------------------------------------------------------------------------------
+# gradient arenas for the mixer's split() views
+# ------------------------------------------------------------------------------------------------
+class MixerGradPlan:
+    """One per MambaBlock.forward call.  The mixer splits two GEMM outputs into views (xz -> x | z, x_dbl ->
+    dt | B | C); autograd's backward of a split is a concatenation of the parts' gradients.  With a plan the kernels
+    that PRODUCE those gradients write them straight into the right slice of one buffer per split (the C-ABI takes
+    strided outputs), and split's backward hands that buffer on without a copy.  Everything falls back to the
+    ordinary concatenation if a gradient did not come from the arena."""
+
+    def __init__(self, xz_shape=None, xdbl_shape=None):
+        self.arena = {}
+        self.xz_shape = None if xz_shape is None else tuple(xz_shape)        # [B, L, 2 * d_inner]
+        self.xdbl_shape = None if xdbl_shape is None else tuple(xdbl_shape)  # [B, L, dt_rank + 2 * d_state]
+
+    def buffer(self, key, shape, dtype, device):
+        b = self.arena.get(key)
+        if b is None or b.shape != tuple(shape) or b.dtype != dtype:
+            b = torch.empty(tuple(shape), dtype=dtype, device=device)
+            self.arena[key] = b
+        return b
+
+    def part(self, key, shape, dtype, device, start, width):
+        """The [..., start:start+width] slice of arena `key` (allocated on first use)."""
+        return self.buffer(key, shape, dtype, device)[..., start:start + width]
+
+
+class SplitFn(torch.autograd.Function):
+    """x.split(sizes, dim=-1) whose backward returns the plan's arena when every part's gradient already lives in
+    its slice of it (no concatenation kernel); otherwise the usual cat."""
+
+    @staticmethod
+    def forward(ctx, x, plan, key, *sizes):
+        ctx.plan, ctx.key, ctx.sizes = plan, key, sizes
+        ctx.xshape, ctx.xdtype = x.shape, x.dtype
+        return tuple(v.view_as(v) for v in x.split(list(sizes), dim=-1))
+
+    @staticmethod
+    def backward(ctx, *grads):
+        buf = ctx.plan.arena.get(ctx.key) if ctx.plan is not None else None
+        ok = buf is not None and buf.shape == ctx.xshape and buf.dtype == ctx.xdtype
+        off = 0
+        for g, w in zip(grads, ctx.sizes):
+            if ok:
+                want = buf[..., off:off + w]
+                ok = (g is not None and g.dtype == buf.dtype and g.shape == want.shape and g.stride() == want.stride()
+                      and g.data_ptr() == want.data_ptr())
+            off += w
+        if ok:
+            return (buf, None, None) + (None,) * len(ctx.sizes)
+        parts = [g if g is not None else torch.zeros(ctx.xshape[:-1] + (w,), dtype=ctx.xdtype, device=grads[0].device if grads[0] is not None else None)
+                 for g, w in zip(grads, ctx.sizes)]
+        return (torch.cat([p_.to(ctx.xdtype) for p_ in parts], dim=-1), None, None) + (None,) * len(ctx.sizes)
+
+
+def split_fn(x, sizes, plan=None, key=None):
+    if plan is None:
+        return x.split(list(sizes), dim=-1)
+    return SplitFn.apply(x, plan, key, *sizes)
+
+
+# ------------------------------------------------------------------------------------------------
 # selective scan
 # ------------------------------------------------------------------------------------------------
 def _scan_fwd_raw(u, delta, A, B, C, D, z, delta_bias, delta_softplus, ckpt, chunk, h_init=None, h_last=None,
@@ -119,8 +180,9 @@ def _scan_fwd_raw(u, delta, A, B, C, D, z, delta_bias, delta_softplus, ckpt, chu
 
 class SelectiveScanFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, u, delta, A, B, C, D, z, delta_bias, delta_softplus, chunk, a_is_log=False):
+    def forward(ctx, u, delta, A, B, C, D, z, delta_bias, delta_softplus, chunk, a_is_log=False, plan=None):
         _require_cuda(u, delta, A, B, C, D, z, delta_bias)
+        ctx.plan = plan
         if u.dim() != 3 or delta.shape != u.shape:
             raise ValueError(f"selective_scan: u {tuple(u.shape)} and delta {tuple(delta.shape)} must be equal [B, L, D]")
         if A.dim() != 2 or A.shape[0] != u.shape[2]:
@@ -157,9 +219,17 @@ class SelectiveScanFn(torch.autograd.Function):
         dev = u.device
         du = torch.empty_like(u, memory_format=torch.contiguous_format)
         ddelta = torch.empty((Bsz, L, Dm), dtype=u.dtype, device=dev)
-        dz = torch.empty((Bsz, L, Dm), dtype=u.dtype, device=dev) if z is not None else None
-        dB = torch.empty((Bsz, L, N), dtype=u.dtype, device=dev)
-        dC = torch.empty((Bsz, L, N), dtype=u.dtype, device=dev)
+        plan = ctx.plan
+        if plan is not None and z is not None and plan.xz_shape is not None and plan.xdbl_shape is not None:
+            # gradients of the split() views go straight into their slices of the arenas (see MixerGradPlan)
+            dz = plan.part("xz", plan.xz_shape, u.dtype, dev, Dm, Dm)
+            R = plan.xdbl_shape[-1] - 2 * N
+            dB = plan.part("xdbl", plan.xdbl_shape, u.dtype, dev, R, N)
+            dC = plan.part("xdbl", plan.xdbl_shape, u.dtype, dev, R + N, N)
+        else:
+            dz = torch.empty((Bsz, L, Dm), dtype=u.dtype, device=dev) if z is not None else None
+            dB = torch.empty((Bsz, L, N), dtype=u.dtype, device=dev)
+            dC = torch.empty((Bsz, L, N), dtype=u.dtype, device=dev)
         dA = torch.empty((Dm, N), dtype=torch.float32, device=dev)
         dD = torch.empty((Dm,), dtype=torch.float32, device=dev) if D is not None else None
         ddb = torch.empty((Dm,), dtype=torch.float32, device=dev) if dbias is not None else None
@@ -196,19 +266,19 @@ class SelectiveScanFn(torch.autograd.Function):
         _call("mamba_scan_bwd", a, dev)
         tA, tD, tb = ctx.in_dtypes
         return (du, ddelta, dA.to(tA), dB, dC, None if dD is None else dD.to(tD), dz,
-                None if ddb is None else ddb.to(tb), None, None, None)
+                None if ddb is None else ddb.to(tb), None, None, None, None)
 
 
 
 
 def selective_scan_fn(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus=False, chunk=None,
-                      A_is_log=False):
+                      A_is_log=False, plan=None):
     """Fused selective scan.  u, delta: [B, L, D]; A: [D, N]; B, C: [B, L, N]; D, delta_bias: [D];
     z: [B, L, D].  Returns out [B, L, D] = (scan(u, delta, A, B, C) + D*u) * silu(z).
     A_is_log: `A` is the A_log parameter; the kernels form A = -exp(A_log) (simple_mamba @L270) themselves and the
     gradient comes back w.r.t. A_log (saves five elementwise launches per layer and step)."""
     return SelectiveScanFn.apply(u, delta, A, B, C, D, z, delta_bias, bool(delta_softplus),
-                                 SCAN_CHUNK if chunk is None else int(chunk), bool(A_is_log))
+                                 SCAN_CHUNK if chunk is None else int(chunk), bool(A_is_log), plan)
 
 
 def selective_scan_prefill(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus=False, h_init=None):
@@ -239,8 +309,9 @@ def _conv_args(x, w2, bias, K):
 
 class CausalConv1dSiluFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias):
+    def forward(ctx, x, weight, bias, plan=None):
         _require_cuda(x, weight, bias)
+        ctx.plan = plan
         D = x.shape[2]
         K = weight.shape[-1]
         if weight.numel() != D * K:
@@ -264,7 +335,11 @@ class CausalConv1dSiluFn(torch.autograd.Function):
         Bsz, L, D = x.shape
         K = w2.shape[1]
         dout = _rows(dout.to(x.dtype))
-        dx = torch.empty((Bsz, L, D), dtype=x.dtype, device=x.device)
+        plan = ctx.plan
+        if plan is not None and plan.xz_shape is not None and plan.xz_shape[-1] == 2 * D:
+            dx = plan.part("xz", plan.xz_shape, x.dtype, x.device, 0, D)   # first half of d(xz)
+        else:
+            dx = torch.empty((Bsz, L, D), dtype=x.dtype, device=x.device)
         dw = torch.empty((D, K), dtype=torch.float32, device=x.device)
         db = torch.empty((D,), dtype=torch.float32, device=x.device) if b32 is not None else None
         wsb = lib().mamba_conv1d_bwd_workspace_bytes(Bsz, L, D, K)
@@ -275,12 +350,12 @@ class CausalConv1dSiluFn(torch.autograd.Function):
         a.dweight, a.dbias = _p(dw), _p(db)
         a.workspace, a.workspace_bytes = _p(ws), wsb
         _call("mamba_conv1d_silu_bwd", a, x.device)
-        return dx, dw.view(ctx.wshape).to(ctx.wdtype), None if db is None else db.to(ctx.bdtype)
+        return dx, dw.view(ctx.wshape).to(ctx.wdtype), None if db is None else db.to(ctx.bdtype), None
 
 
-def causal_conv1d_silu_fn(x, weight, bias=None):
+def causal_conv1d_silu_fn(x, weight, bias=None, plan=None):
     """silu(depthwise causal conv1d(x)) for x [B, L, D] (channels last); weight [D, 1, K] or [D, K]."""
-    return CausalConv1dSiluFn.apply(x, weight, bias)
+    return CausalConv1dSiluFn.apply(x, weight, bias, plan)
 
 
 def causal_conv1d_silu_prefill(x, weight, bias=None):
