@@ -86,3 +86,33 @@ def test_block_init_matches_reference_init():
 def test_default_model_param_count():
     m = train.new_model("mamba")
     assert sum(p.numel() for p in m.parameters()) == 88554496 - 6 * 1024  # unpadded vocabulary
+
+
+def test_split_fn_backward_uses_the_arena_or_falls_back_to_cat():
+    """ops.SplitFn (pure torch): when every part's gradient already lives in its slice of the plan's arena the
+    backward returns the arena itself (no concatenation); any other gradient takes the ordinary cat path."""
+    from mamba_b200 import ops
+    torch.manual_seed(0)
+    x = torch.randn(2, 5, 7, requires_grad=True)
+    # (1) gradients produced elsewhere -> cat fallback, equal to plain split()
+    plan = ops.MixerGradPlan(x.shape, None)
+    a, b = ops.split_fn(x, [3, 4], plan, "xz")
+    ga, gb = torch.randn(2, 5, 3), torch.randn(2, 5, 4)
+    (gx,) = torch.autograd.grad([a, b], [x], [ga, gb])
+    assert torch.equal(gx, torch.cat([ga, gb], dim=-1))
+    # (2) gradients that ARE the arena's slices -> the arena comes back untouched
+    plan = ops.MixerGradPlan(x.shape, None)
+    a, b = ops.split_fn(x, [3, 4], plan, "xz")
+    pa = plan.part("xz", x.shape, x.dtype, x.device, 0, 3)
+    pb = plan.part("xz", x.shape, x.dtype, x.device, 3, 4)
+    pa.copy_(ga), pb.copy_(gb)
+    (gx,) = torch.autograd.grad([a, b], [x], [pa, pb])
+    assert gx.data_ptr() == plan.arena["xz"].data_ptr() and torch.equal(gx, torch.cat([ga, gb], dim=-1))
+    # (3) one part missing (None gradient) -> zeros for it
+    plan = ops.MixerGradPlan(x.shape, None)
+    a, b = ops.split_fn(x, [3, 4], plan, "xz")
+    (gx,) = torch.autograd.grad([a], [x], [ga])
+    assert torch.equal(gx, torch.cat([ga, torch.zeros(2, 5, 4)], dim=-1))
+    # without a plan it is torch's own split
+    a, b = ops.split_fn(x, [3, 4])
+    assert a.shape == (2, 5, 3) and b.shape == (2, 5, 4)
