@@ -91,6 +91,46 @@ class AsyncWgrad:
             torch.cuda.current_stream(cls.stream.device).wait_stream(cls.stream)
 
 
+class WeightShadows:
+    """Autocast-dtype copies of the mixer's linear weights, kept by a Trainer.  Under autocast every forward casts
+    each fp32 weight matrix (41 launches on the critical path of the step); a Trainer that owns the optimizer can
+    instead refresh a persistent copy right after it has updated the parameter — on its side stream, under the
+    backward.  A copy is used only while the parameter's version counter still is the one it was made from, so any
+    other writer (load_state_dict, a user's in-place edit) silently falls back to the cast."""
+    table = {}   # id(param) -> [shadow, version, weakref(param)]
+
+    @classmethod
+    def register(cls, params, dtype):
+        """Returns the shadow tensors (the caller keeps them alive for as long as its CUDA graph may use them)."""
+        import weakref
+        cls.table = {k: e for k, e in cls.table.items() if e[2]() is not None}   # drop entries of dead parameters
+        for p in params:
+            cls.table[id(p)] = [torch.empty_like(p, dtype=dtype), -1, weakref.ref(p)]
+        cls.refresh(params)
+        return [cls.table[id(p)][0] for p in params]
+
+    @classmethod
+    def refresh(cls, params):
+        ps = [p for p in params if id(p) in cls.table]
+        if not ps:
+            return
+        with torch.no_grad():
+            torch._foreach_copy_([cls.table[id(p)][0] for p in ps], [p.detach() for p in ps])
+        for p in ps:
+            cls.table[id(p)][1] = p._version
+
+    @classmethod
+    def stale(cls, params):
+        return any(id(p) in cls.table and cls.table[id(p)][1] != p._version for p in params)
+
+    @classmethod
+    def get(cls, w, dtype):
+        e = cls.table.get(id(w))
+        if e is not None and e[2]() is w and e[1] == w._version and e[0].dtype == dtype:
+            return e[0]
+        return None
+
+
 class _LinearFn(torch.autograd.Function):
     """y = x @ W^T in the autocast dtype (cuBLAS plumbing, no arithmetic of its own).  Unlike nn.Linear under
     autocast, the weight gradient leaves the GEMM already in the parameter's dtype (bf16 x bf16 -> fp32 output)
@@ -99,7 +139,9 @@ class _LinearFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, dt, plan=None):
         ctx.plan = plan
-        wc = w.to(dt)
+        wc = WeightShadows.get(w, dt) if WeightShadows.table else None
+        if wc is None:
+            wc = w.to(dt)
         x2 = x.reshape(-1, x.shape[-1])
         if x2.dtype != dt:
             x2 = x2.to(dt)

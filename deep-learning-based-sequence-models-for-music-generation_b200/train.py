@@ -339,8 +339,24 @@ class Trainer:
             self._side = torch.cuda.Stream(device=self.device)
             if self.grads is not None:
                 self.grads._side = self._side
+        # autocast-dtype shadows of the mixer's linear weights, refreshed after each Adam update (off the critical
+        # path) instead of being re-cast in every forward (models.mamba.WeightShadows)
+        self._shadow_params = []
+        if self.device.type == "cuda" and autocast_dtype is not None and os.environ.get("MAMBA_B200_SHADOWS", "1") == "1":
+            from .models.mamba.mamba import MambaBlock, WeightShadows
+            for m in model.modules():
+                if isinstance(m, MambaBlock):
+                    for lin in (m.in_proj, m.x_proj, m.dt_proj, m.out_proj):
+                        if lin.bias is None or lin is m.dt_proj:
+                            self._shadow_params.append(lin.weight)
+            self._shadow_refs = WeightShadows.register(self._shadow_params, autocast_dtype)
         self.use_graph = use_graph
         self.graph = None
+
+    def _refresh_shadows(self, params=None):
+        if self._shadow_params:
+            from .models.mamba.mamba import WeightShadows
+            WeightShadows.refresh(self._shadow_params if params is None else params)
 
     def _flatten_grads(self, bucket_mb):
         # one rank: autograd writes each gradient straight into a fresh buffer (no accumulate-add per parameter);
@@ -391,6 +407,7 @@ class Trainer:
         if self._stage_optimizers is None:
             self.grads.finish()
             self.optimizer.step()
+            self._refresh_shadows()
         else:
             torch.cuda.current_stream(self.device).wait_stream(self._side)
         self.loss.copy_(loss.detach())
@@ -410,6 +427,7 @@ class Trainer:
                 self.grads._world, self.grads._group = self.world_size, self.pg
                 self.grads._reduce_bucket(gi)
             self._stage_optimizers[gi].step()
+            self._refresh_shadows(self._stage_params[gi])
 
     def _zero_grads(self):
         if self.grads is None:
@@ -431,6 +449,7 @@ class Trainer:
         self._join_wgrad()
         self._allreduce()
         self.optimizer.step()
+        self._refresh_shadows()
         self.loss.copy_(loss.detach())
 
     def capture(self, warmup=3):
@@ -456,6 +475,7 @@ class Trainer:
                     for v in st.values():
                         if torch.is_tensor(v):
                             v.zero_()
+            self._refresh_shadows()   # the restore above rewrote the parameters
         torch.cuda.synchronize(self.device)
 
     def step(self, src, trg, meta):
@@ -464,6 +484,10 @@ class Trainer:
         self.src.copy_(src, non_blocking=True)
         self.trg.copy_(trg, non_blocking=True)
         self.meta.copy_(meta, non_blocking=True)
+        if self._shadow_params:   # someone else wrote the parameters (load_state_dict, capture's restore): re-cast
+            from .models.mamba.mamba import WeightShadows
+            if WeightShadows.stale(self._shadow_params):
+                WeightShadows.refresh(self._shadow_params)
         if self.use_graph:
             if self.graph is None:
                 self.capture()

@@ -116,3 +116,22 @@ def test_split_fn_backward_uses_the_arena_or_falls_back_to_cat():
     # without a plan it is torch's own split
     a, b = ops.split_fn(x, [3, 4])
     assert a.shape == (2, 5, 3) and b.shape == (2, 5, 4)
+
+
+def test_weight_shadows_are_used_only_while_the_parameter_is_unchanged():
+    """models.mamba.WeightShadows: a cast copy is handed out only while the parameter's version counter is the one it
+    was made from; any other in-place writer (load_state_dict, optimizer of another owner) makes it fall back."""
+    from mamba_b200.models.mamba.mamba import WeightShadows
+    w = torch.nn.Parameter(torch.randn(4, 6))
+    other = torch.nn.Parameter(torch.randn(4, 6))
+    keep = WeightShadows.register([w], torch.bfloat16)
+    sh = WeightShadows.get(w, torch.bfloat16)
+    assert sh is keep[0] and torch.equal(sh, w.detach().to(torch.bfloat16))
+    assert WeightShadows.get(w, torch.float16) is None and WeightShadows.get(other, torch.bfloat16) is None
+    with torch.no_grad():
+        w.mul_(2.0)                                   # someone else writes the parameter
+    assert WeightShadows.stale([w]) and WeightShadows.get(w, torch.bfloat16) is None
+    WeightShadows.refresh([w])
+    assert not WeightShadows.stale([w])
+    assert torch.equal(WeightShadows.get(w, torch.bfloat16), w.detach().to(torch.bfloat16))
+    WeightShadows.table.pop(id(w))
