@@ -353,6 +353,12 @@ class Trainer:
         self.use_graph = use_graph
         self.graph = None
 
+    @property
+    def optimizers(self):
+        """The Adam instances that actually step: one per stage in the staged step (their union covers every
+        parameter exactly once), otherwise the single `self.optimizer`.  Use this for state_dict()/load_state_dict()."""
+        return list(self._stage_optimizers) if self._stage_optimizers is not None else [self.optimizer]
+
     def _refresh_shadows(self, params=None):
         if self._shadow_params:
             from .models.mamba.mamba import WeightShadows
