@@ -265,9 +265,10 @@ class Trainer:
     on a side stream as soon as each bucket's last gradient is produced.
     """
 
-    # overlap_allreduce: launch each gradient bucket's all-reduce from backward hooks on a side stream.  Verified
-    # on CPU/gloo (tests/test_dist_cpu.py); under NCCL + CUDA-graph capture it hung on the 2-GPU box in round 1, so
-    # the default is the plain post-backward exchange (92-97 % weak-scaling efficiency at 8 GPUs as measured).
+    # stages: the default overlap — staged backward, per-stage all-reduce + Adam on a side stream, issued from the
+    # capturing thread (see __init__).  overlap_allreduce: the older hook-driven variant (each bucket's all-reduce
+    # launched from autograd's post-accumulate hooks); verified on CPU/gloo (tests/test_dist_cpu.py), but under
+    # NCCL + CUDA-graph capture it hung on the 2-GPU box, so it stays off.
     def __init__(self, model, lr=None, autocast_dtype=torch.bfloat16, world_size=1, process_group=None,
                  batch_size=None, block_len=None, use_graph=True, bucket_mb=64, overlap_allreduce=False,
                  async_wgrad=None, stages=None):
