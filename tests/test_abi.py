@@ -57,6 +57,25 @@ def test_ctypes_struct_layout_matches_c(tmp_path):
             assert int(got[f"{cname}.{fname}"]) == getattr(ct, fname).offset, f"{cname}.{fname}"
 
 
+def test_flag_and_dtype_constants_match_the_header(tmp_path):
+    """The python mirrors of the header's enums (flags, dtypes) are compiled against the header itself."""
+    from mamba_b200 import _lib
+    names = {"MAMBA_FLAG_HAS_Z": _lib.FLAG_HAS_Z, "MAMBA_FLAG_DELTA_SOFTPLUS": _lib.FLAG_DELTA_SOFTPLUS,
+             "MAMBA_FLAG_HAS_DELTA_BIAS": _lib.FLAG_HAS_DELTA_BIAS, "MAMBA_FLAG_HAS_D": _lib.FLAG_HAS_D,
+             "MAMBA_FLAG_A_IS_LOG": _lib.FLAG_A_IS_LOG, "MAMBA_F32": _lib.MAMBA_F32, "MAMBA_BF16": _lib.MAMBA_BF16}
+    lines = ['#include <stdio.h>', f'#include "{HEADER}"', "int main(void){"]
+    lines += [f'printf("{n} %d\\n", (int){n});' for n in names]
+    lines.append("return 0;}")
+    src = tmp_path / "consts.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "consts"
+    subprocess.run(["gcc", "-std=c99", "-o", str(exe), str(src)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    got = dict(l.split() for l in out.strip().splitlines())
+    for n, v in names.items():
+        assert int(got[n]) == v, n
+
+
 def test_argument_validation_without_gpu(lib):
     """Bad arguments are rejected before any CUDA call, with a message (error behaviour of the boundary)."""
     from mamba_b200 import _lib
