@@ -208,4 +208,22 @@ __host__ __device__ __forceinline__ bool aligned16(const void* p) { return (rein
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// Opt-in to more than 48 KB of dynamic shared memory.  The attribute is per (function, DEVICE): the cache is keyed by
+// the current device so that one host thread driving several GPUs configures each of them (one `static thread_local
+// SmemConfig` per kernel instantiation at the call site).
+constexpr int kMaxDevices = 64;
+struct SmemConfig {
+  size_t bytes[kMaxDevices] = {};
+};
+template <typename K>
+static inline int ensure_dynamic_smem(K kern, size_t smem, SmemConfig& cfg, const char* what) {
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = -1;
+  if (dev >= 0 && smem <= cfg.bytes[dev]) return MAMBA_OK;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return set_error(MAMBA_ELAUNCH, "%s: cudaFuncSetAttribute(%zu B): %s", what, smem, cudaGetErrorString(e));
+  if (dev >= 0) cfg.bytes[dev] = smem;
+  return MAMBA_OK;
+}
+
 }  // namespace mb

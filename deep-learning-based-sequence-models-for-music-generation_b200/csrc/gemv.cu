@@ -138,12 +138,9 @@ template <typename TX, typename TW, int BT, int ROWS, int GW>
 static int gemv_launch_cfg(const GemvParams& p, cudaStream_t st) {
   const size_t smem = (size_t)BT * p.K * 4;
   auto kern = gemv_kernel<TX, TW, BT, ROWS, GW>;
-  static thread_local size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return set_error(MAMBA_ELAUNCH, "linear_step: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    configured = smem;
-  }
+  static thread_local SmemConfig cfg;
+  if (smem > 48 * 1024)
+    if (int rc = ensure_dynamic_smem(kern, smem, cfg, "linear_step")) return rc;
   const int rows_per_block = (kGemvThreads / GW) * ROWS;
   int blocks = ceil_div(p.N, rows_per_block);
   const int per_sm = smem > 100 * 1024 ? 1 : (smem > 50 * 1024 ? 2 : 4);

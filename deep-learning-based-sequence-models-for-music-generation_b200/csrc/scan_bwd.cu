@@ -603,12 +603,8 @@ static int launch_bwd(const ScanBwdParams& p, cudaStream_t stream) {
   if (smem > 227 * 1024)
     return set_error(MAMBA_ESIZE, "scan_bwd: d_state %d needs %zu B of shared memory", p.N, smem);
   auto kern = scan_bwd_kernel<T, NPER, NW, kCK>;
-  static thread_local size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return set_error(MAMBA_ELAUNCH, "scan_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    configured = smem;
-  }
+  static thread_local SmemConfig cfg;
+  if (int rc = ensure_dynamic_smem(kern, smem, cfg, "scan_bwd")) return rc;
   dim3 grid(p.ntiles, p.B);
   kern<<<grid, (NW + kBHelperWarps) * 32, smem, stream>>>(p);
   count_launch();

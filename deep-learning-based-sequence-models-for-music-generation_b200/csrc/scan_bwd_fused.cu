@@ -624,12 +624,8 @@ static int launch_fused(const ScanBwdParams& p, cudaStream_t stream) {
   const size_t smem = (size_t)FusedLayout<T, NW, kCK>::total;
   if (smem > 227 * 1024) return set_error(MAMBA_ESIZE, "scan_bwd (fused): needs %zu B of shared memory", smem);
   auto kern = scan_bwd_fused_kernel<T, NW, kCK>;
-  static thread_local bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return set_error(MAMBA_ELAUNCH, "scan_bwd (fused): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    configured = true;
-  }
+  static thread_local SmemConfig cfg;
+  if (int rc = ensure_dynamic_smem(kern, smem, cfg, "scan_bwd (fused)")) return rc;
   dim3 grid(p.ntiles, p.B);
   kern<<<grid, (NW + kBHelperWarps) * 32, smem, stream>>>(p);
   count_launch();

@@ -401,12 +401,8 @@ static int launch_fwd(const ScanFwdParams& p, cudaStream_t stream) {
   const size_t smem = fwd_smem_bytes<T>(p.NS, p.NPT, RR);
   if (smem > 227 * 1024) return set_error(MAMBA_ESIZE, "scan_fwd: d_state %d needs %zu B of shared memory", p.N, smem);
   auto kern = scan_fwd_kernel<T, NPER, RR, CKI>;
-  static thread_local size_t configured = 0;  // per instantiation: raise the dynamic-smem limit once per size
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return set_error(MAMBA_ELAUNCH, "scan_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    configured = smem;
-  }
+  static thread_local SmemConfig cfg;  // per instantiation and device: raise the dynamic-smem limit once per size
+  if (int rc = ensure_dynamic_smem(kern, smem, cfg, "scan_fwd")) return rc;
   dim3 grid(ceil_div(p.D, kDT), p.B);
   kern<<<grid, (p.NS + kHelperWarps) * 32, smem, stream>>>(p);
   count_launch();

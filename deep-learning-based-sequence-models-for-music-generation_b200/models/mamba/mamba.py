@@ -1,7 +1,7 @@
 """Drop-in mirror of the reference's Mamba modules, running on the sm_100a kernels of libmamba_b200.so.
 
-Same class names, constructor arguments, parameter names/shapes (hence state_dict layout) and call
-signatures as the reference:
+Same class names, constructor arguments and call signatures as the reference; parameter names/shapes (hence
+state_dict layout) are identical for Layout P and for the OUTER keys of Layout S only — see the warning below:
   * `ModelArgs`, `Mamba(params)`, `ResidualBlock`, `MambaBlock`, `RMSNorm` — the pure-PyTorch Mamba-1 of
     models/mamba/__pycache__/simple_mamba.cpython-311.pyc (source deleted upstream; SURVEY.md Appendix A;
     `@Lnnn` = original source line).  "Layout P": keys embedding / metadata_embedding /
@@ -10,6 +10,10 @@ signatures as the reference:
     keys token_embedding / metadata_embedding / output_layer / layers.{i}.* / norm; no residuals, final
     LayerNorm, untied head with bias.  Its layers here are `MambaBlock`s (the Mamba-1 maths that
     BASELINE.json's north_star names); the external mamba_ssm.Mamba2 it stacks upstream is out of scope.
+    NOT CHECKPOINT-COMPATIBLE with the reference's shipped model: upstream `layers.{i}` are Mamba2 modules
+    (in_proj [4256,1024], conv1d over 2176 channels, A_log/D/dt_bias [32], gated norm — SURVEY Appendix B), here
+    they are Mamba-1 blocks (x_proj, dt_proj, A_log [2048,64]); the constructor warns once about it and
+    `load_state_dict` of a reference checkpoint fails on the layer keys by design.
 Both forms take `forward(tokens[B,T] long, meta[B,6] long)` and return logits `[B, T, V]` (first 6
 positions dropped, mamba.py:35 / simple_mamba @L96).
 
@@ -23,7 +27,9 @@ recurrent decode that replaces the full re-forward per token of scripts/generate
 """
 from __future__ import annotations
 
+import contextlib
 import math
+import warnings
 from dataclasses import dataclass
 from types import SimpleNamespace
 from typing import Union
@@ -72,23 +78,31 @@ def _act_dtype(x: torch.Tensor) -> torch.dtype:
 class AsyncWgrad:
     """Weight-gradient GEMMs on a side stream.  The scan kernels put one CTA on 128 of the 148 SMs for most of the
     backward; a weight gradient is needed only by the optimizer, so `_LinearFn.backward` can write it straight into
-    `param.grad` on a second stream, where it runs on the SMs the scans leave idle.  `join()` (before the
-    optimizer) makes the current stream wait for it.  Works eagerly and under CUDA-graph capture (the fork/join
-    becomes graph edges); off unless a Trainer turns it on."""
+    `param.grad` on a second stream, where it runs on the SMs the scans leave idle.
+
+    The side path OVERWRITES param.grad and returns no gradient to autograd, so it is safe only for an owner that
+    (i) pre-allocates the gradient buffers, (ii) joins the stream before anything reads them and (iii) never
+    accumulates over micro-batches.  It is therefore scoped: active only inside `with AsyncWgrad.scope(stream,
+    ids)` — which a Trainer opens around ITS OWN backward calls, naming ITS parameters — and off everywhere else
+    (train.train_step, a second model, gradient accumulation all take the ordinary autograd path).  Works eagerly
+    and under CUDA-graph capture (the fork/join becomes graph edges).  The flag is process-wide rather than
+    thread-local because autograd runs CUDA backward nodes on its own device threads."""
     stream = None
+    owned = frozenset()   # ids of the parameters of the scope's owner
 
     @classmethod
-    def enable(cls, device):
-        cls.stream = torch.cuda.Stream(device=device)
+    @contextlib.contextmanager
+    def scope(cls, stream, param_ids):
+        prev = (cls.stream, cls.owned)
+        cls.stream, cls.owned = stream, param_ids
+        try:
+            yield
+        finally:
+            cls.stream, cls.owned = prev
 
     @classmethod
     def disable(cls):
-        cls.stream = None
-
-    @classmethod
-    def join(cls):
-        if cls.stream is not None:
-            torch.cuda.current_stream(cls.stream.device).wait_stream(cls.stream)
+        cls.stream, cls.owned = None, frozenset()
 
 
 class WeightShadows:
@@ -173,8 +187,8 @@ class _LinearFn(torch.autograd.Function):
                     dx = dx.to(xdt)
         if ctx.needs_input_grad[1]:
             side, p = AsyncWgrad.stream, ctx.param
-            if (side is not None and p is not None and p.grad is not None and p.grad.dtype == wdt
-                    and p.grad.is_contiguous() and wdt != g2.dtype):
+            if (side is not None and p is not None and id(p) in AsyncWgrad.owned and p.grad is not None
+                    and p.grad.dtype == wdt and p.grad.is_contiguous() and wdt != g2.dtype):
                 # straight into param.grad on the side stream (this layer is the parameter's only user)
                 cur = torch.cuda.current_stream(g2.device)
                 side.wait_stream(cur)
@@ -376,6 +390,11 @@ class Mamba(nn.Module):
         super().__init__()
         if isinstance(d_model, int):
             self.layout = "S"
+            warnings.warn(
+                "mamba_b200.Mamba(d_model, n_layers): the shipped wrapper's signature and OUTER state_dict keys, but its "
+                "layers are Mamba-1 blocks (the hot path BASELINE.json names), not mamba_ssm.Mamba2: checkpoints of the "
+                "reference's shipped model do not load into it and its outputs differ.  Use Mamba(get_mamba_dict()) "
+                "(Layout P) for the checkpoint-compatible pure-PyTorch Mamba-1.", stacklevel=2)
             params = _params_from_configs(d_model, n_layers)
             self.params = params
             self.token_embedding = nn.Embedding(cc.vocab_size, d_model)            # mamba.py:12

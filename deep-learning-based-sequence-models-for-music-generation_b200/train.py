@@ -304,6 +304,11 @@ class Trainer:
             seen |= {id(p) for p in model.norm_f.parameters()}
             groups[0] = groups[0] + [p for p in model.parameters() if id(p) not in seen]
             self._stage_params = [[p for p in g if p.requires_grad] for g in groups]
+        # DDP broadcasts rank 0's parameters and buffers at construction (train_parallel.py:151); do the same, so that
+        # ranks that seeded differently (or loaded different checkpoints) cannot apply averaged gradients to
+        # different weights
+        if world_size > 1:
+            self._broadcast_parameters()
         self._flatten_grads(bucket_mb)
         # weight-gradient GEMMs of the mixer's linear layers on a side stream (models.mamba.AsyncWgrad): needs
         # autocast (the fp32-output GEMM path) and gradient buffers that exist before backward
@@ -312,10 +317,10 @@ class Trainer:
         if async_wgrad is None:
             async_wgrad = os.environ.get("MAMBA_B200_ASYNC_WGRAD", "1") == "1"
         self.async_wgrad = bool(async_wgrad) and self.device.type == "cuda" and autocast_dtype is not None
-        self._wgrad_params = []
+        self._wgrad_params, self._wgrad_stream = [], None
         if self.async_wgrad:
-            from .models.mamba.mamba import AsyncWgrad, MambaBlock
-            AsyncWgrad.enable(self.device)
+            from .models.mamba.mamba import MambaBlock
+            self._wgrad_stream = torch.cuda.Stream(device=self.device)
             for m in model.modules():
                 if isinstance(m, MambaBlock):
                     for lin in (m.in_proj, m.x_proj, m.dt_proj, m.out_proj):
@@ -324,6 +329,14 @@ class Trainer:
             if self.grads is None:
                 for p in self._wgrad_params:
                     p.grad = torch.zeros_like(p)
+        self._wgrad_ids = frozenset(id(p) for p in self._wgrad_params)
+        # the hook-driven overlap and the staged step both exchange every bucket: together they would reduce twice
+        # (gradients scaled by 1/world^2), so the staged step wins and the hooks are not armed
+        if overlap_allreduce and self._stage_groups is not None:
+            import warnings
+            warnings.warn("Trainer: overlap_allreduce is ignored when the staged step is active (stages > 1); "
+                          "pass stages=1 to use the hook-driven overlap")
+            overlap_allreduce = False
         self.overlap = overlap_allreduce and world_size > 1
         if self.overlap:
             self.grads.overlap_with_backward(world_size, process_group)
@@ -385,8 +398,35 @@ class Trainer:
 
     def _join_wgrad(self):
         if self.async_wgrad:
-            from .models.mamba.mamba import AsyncWgrad
-            AsyncWgrad.join()
+            torch.cuda.current_stream(self.device).wait_stream(self._wgrad_stream)
+
+    def _wgrad_scope(self):
+        """Context in which this Trainer's backward may write ITS weight gradients on the side stream."""
+        if not self.async_wgrad:
+            import contextlib
+            return contextlib.nullcontext()
+        from .models.mamba.mamba import AsyncWgrad
+        return AsyncWgrad.scope(self._wgrad_stream, self._wgrad_ids)
+
+    def _broadcast_parameters(self):
+        """Rank 0's parameters and buffers to every rank, one flat collective per dtype."""
+        import torch.distributed as dist
+        with torch.no_grad():
+            by_dtype = {}
+            for t in list(self.model.parameters()) + list(self.model.buffers()):
+                by_dtype.setdefault(t.dtype, []).append(t)
+            for ts in by_dtype.values():
+                seen, uniq = set(), []
+                for t in ts:   # tied parameters appear once
+                    if t.data_ptr() not in seen:
+                        seen.add(t.data_ptr())
+                        uniq.append(t)
+                flat = torch.cat([t.detach().reshape(-1) for t in uniq])
+                dist.broadcast(flat, src=dist.get_global_rank(self.pg, 0) if self.pg is not None else 0, group=self.pg)
+                off = 0
+                for t in uniq:
+                    t.copy_(flat[off:off + t.numel()].view_as(t))
+                    off += t.numel()
 
     def _step_body_staged(self):
         m, groups = self.model, self._stage_groups
@@ -405,11 +445,13 @@ class Trainer:
             output = m._head(normed[:, self.meta.shape[-1]:])
         loss = loss_fn(self.src, self.trg, output)
         self._zero_grads()
-        loss.backward()
+        with self._wgrad_scope():
+            loss.backward()
         self._finish_stage(len(groups) - 1)
         for gi in range(len(cuts) - 1, -1, -1):
             r, h, rd, hd = cuts[gi]
-            torch.autograd.backward([r, h], [rd.grad, hd.grad])
+            with self._wgrad_scope():
+                torch.autograd.backward([r, h], [rd.grad, hd.grad])
             self._finish_stage(gi)
         if self._stage_optimizers is None:
             self.grads.finish()
@@ -427,8 +469,7 @@ class Trainer:
             return
         self._side.wait_stream(torch.cuda.current_stream(self.device))
         if self.async_wgrad:   # the stage's side-stream weight gradients must be in place too; the main stream need
-            from .models.mamba.mamba import AsyncWgrad   # not wait for them
-            self._side.wait_stream(AsyncWgrad.stream)
+            self._side.wait_stream(self._wgrad_stream)   # not wait for them
         with torch.cuda.stream(self._side):
             if self.grads is not None and self.world_size > 1:
                 self.grads._world, self.grads._group = self.world_size, self.pg
@@ -452,7 +493,8 @@ class Trainer:
             output = self.model(self.src, self.meta)
         loss = loss_fn(self.src, self.trg, output)
         self._zero_grads()
-        loss.backward()
+        with self._wgrad_scope():
+            loss.backward()
         self._join_wgrad()
         self._allreduce()
         self.optimizer.step()
@@ -463,6 +505,12 @@ class Trainer:
         """Warm up on a side stream, capture one step, then put parameters and Adam state back to where they
         were: capturing must not train."""
         saved = [p.detach().clone() for p in self.model.parameters()]
+        opts = [self.optimizer] + (self._stage_optimizers or [])
+        # Adam state that exists BEFORE the warm-up (a resume: Trainer.optimizers[i].load_state_dict(...)) is put back
+        # afterwards; state the warm-up itself creates is zeroed.  Keyed by (optimizer, parameter, state name).
+        saved_state = {(oi, id(p), k): v.detach().clone()
+                       for oi, opt in enumerate(opts) for p, st in opt.state.items()
+                       for k, v in st.items() if torch.is_tensor(v)}
         s = torch.cuda.Stream(device=self.device)
         s.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(s):
@@ -477,11 +525,15 @@ class Trainer:
         with torch.no_grad():
             for p, q in zip(self.model.parameters(), saved):
                 p.copy_(q)
-            for opt in [self.optimizer] + (self._stage_optimizers or []):
-                for st in opt.state.values():   # exp_avg, exp_avg_sq and the device-side step counter
-                    for v in st.values():
+            for oi, opt in enumerate(opts):
+                for p, st in opt.state.items():   # exp_avg, exp_avg_sq and the device-side step counter
+                    for k, v in st.items():
                         if torch.is_tensor(v):
-                            v.zero_()
+                            old = saved_state.get((oi, id(p), k))
+                            if old is None:
+                                v.zero_()
+                            else:
+                                v.copy_(old)
             self._refresh_shadows()   # the restore above rewrote the parameters
         torch.cuda.synchronize(self.device)
 

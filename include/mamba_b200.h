@@ -12,8 +12,11 @@
  *  - plain pointers and sizes only; no torch types.  All pointers are DEVICE pointers unless
  *    the name ends in `_host`.
  *  - the caller owns and allocates every input, output and workspace buffer; the library
- *    keeps no global state, never allocates, never synchronises, and enqueues all work on the
- *    `stream` argument (a `cudaStream_t` passed as `void*`).
+ *    never allocates, never synchronises, and enqueues all work on the `stream` argument (a
+ *    `cudaStream_t` passed as `void*`) of the CURRENT device.  Process-wide state is limited to
+ *    the monotonic launch counter behind mamba_launch_count(); per-thread state to the last
+ *    error message and a per-device record of which kernels have had their dynamic
+ *    shared-memory limit raised (so one host thread may drive several devices in turn).
  *  - activations are row-major `[batch, seqlen, channels]` with the channel axis contiguous;
  *    `*_bs` / `*_ls` are the batch and sequence strides IN ELEMENTS, so the split views the
  *    reference takes of `in_proj(x)` and `x_proj(x)` are consumed without a copy.

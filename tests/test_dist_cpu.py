@@ -143,7 +143,9 @@ def _staged_worker(rank, world, port, q):
         train.loss_fn = train.loss_fn_torch          # the fused loss is CUDA-only; same function in torch ops
         out = []
         for stages in (1, 2, 4):
-            torch.manual_seed(0)
+            # every rank builds DIFFERENT initial weights: Trainer must broadcast rank 0's (DDP semantics,
+            # train_parallel.py:151), otherwise the ranks would not agree at the end
+            torch.manual_seed(7 * rank)
             model = _FakeMamba()
             tr = train.Trainer(model, lr=1e-2, autocast_dtype=None, world_size=world, batch_size=2, block_len=12,
                                use_graph=False, stages=stages)

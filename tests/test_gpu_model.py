@@ -238,11 +238,12 @@ def test_side_stream_weight_gradients_equal_inline_ones(use_graph):
     b.load_state_dict(a.state_dict())
     try:
         ta = train.Trainer(a, lr=1e-3, batch_size=2, block_len=48, use_graph=use_graph, async_wgrad=False)
-        assert AsyncWgrad.stream is None or not ta.async_wgrad
-        AsyncWgrad.disable()
+        assert not ta.async_wgrad and ta._wgrad_stream is None
         la = [ta.step(*(t.cuda() for t in synthetic.batch(2, 48, seed=30 + i))).item() for i in range(3)]
         tb = train.Trainer(b, lr=1e-3, batch_size=2, block_len=48, use_graph=use_graph, async_wgrad=True)
-        assert tb.async_wgrad and AsyncWgrad.stream is not None and len(tb._wgrad_params) == 4 * 2
+        assert tb.async_wgrad and tb._wgrad_stream is not None and len(tb._wgrad_params) == 4 * 2
+        # the side-stream path is scoped to the Trainer's own backward: nothing is armed process-wide
+        assert AsyncWgrad.stream is None and not AsyncWgrad.owned
         lb = [tb.step(*(t.cuda() for t in synthetic.batch(2, 48, seed=30 + i))).item() for i in range(3)]
     finally:
         AsyncWgrad.disable()
@@ -341,3 +342,64 @@ def _golden_randomise(module, seed):  # identical to tests/golden/make_golden.py
                 p.add_(0.1 * torch.randn(p.shape, generator=g))
             else:
                 p.add_(0.02 * torch.randn(p.shape, generator=g))
+
+
+def test_trainer_resume_keeps_loaded_adam_state_through_capture():
+    """Trainer.capture() (lazy, on the first step) must not wipe optimizer state loaded through
+    Trainer.optimizers[i].load_state_dict() — the documented resume path.  Train 2 steps, save parameters and Adam
+    state, build a fresh graph-captured Trainer from them, step once more: same result as continuing."""
+    from mamba_b200 import synthetic, train
+    from mamba_b200.models.mamba import Mamba, ModelArgs
+    torch.manual_seed(0)
+    a = Mamba(_args(ModelArgs, d_model=64, d_state=64, n_layer=4)).cuda()
+    ta = train.Trainer(a, lr=1e-3, batch_size=2, block_len=40, use_graph=True, stages=2)
+    batches = [[t.cuda() for t in synthetic.batch(2, 40, seed=60 + i)] for i in range(3)]
+    for i in range(2):
+        ta.step(*batches[i])
+    torch.cuda.synchronize()
+    model_sd = {k: v.clone() for k, v in a.state_dict().items()}
+    opt_sd = [o.state_dict() for o in ta.optimizers]
+    import copy
+    opt_sd = copy.deepcopy(opt_sd)
+    la = ta.step(*batches[2]).item()
+
+    b = Mamba(_args(ModelArgs, d_model=64, d_state=64, n_layer=4)).cuda()
+    b.load_state_dict(model_sd)
+    tb = train.Trainer(b, lr=1e-3, batch_size=2, block_len=40, use_graph=True, stages=2)
+    for o, sd in zip(tb.optimizers, opt_sd):
+        o.load_state_dict(sd)
+    lb = tb.step(*batches[2]).item()
+    assert la == lb, (la, lb)
+    for (n1, p1), (n2, p2) in zip(a.named_parameters(), b.named_parameters()):
+        assert_close(p2, p1, 1e-6, 1e-7, what=f"param {n1} after the resumed step")
+    # the resumed optimizer's step counter went from 2 to 3, not from 0 to 1
+    steps = {float(st["step"]) for o in tb.optimizers for st in o.state.values()}
+    assert steps == {3.0}, steps
+
+
+def test_side_stream_wgrad_is_scoped_to_its_trainer():
+    """with a Trainer alive (async weight gradients on), a plain train_step on ANOTHER model — and
+    gradient accumulation over two micro-batches — must take the ordinary autograd path: gradients accumulate."""
+    from mamba_b200 import synthetic, train
+    from mamba_b200.models.mamba import Mamba, ModelArgs
+    from mamba_b200.models.mamba.mamba import AsyncWgrad
+    torch.manual_seed(0)
+    owner = Mamba(_args(ModelArgs, d_model=64, d_state=64)).cuda()
+    tr = train.Trainer(owner, lr=1e-3, batch_size=2, block_len=32, use_graph=False, async_wgrad=True)
+    tr.step(*(t.cuda() for t in synthetic.batch(2, 32, seed=70)))
+    assert tr.async_wgrad and AsyncWgrad.stream is None
+    other = Mamba(_args(ModelArgs, d_model=64, d_state=64)).cuda()
+    src, trg, meta = (t.cuda() for t in synthetic.batch(2, 32, seed=71))
+
+    def grads_after(n_micro):
+        other.zero_grad(set_to_none=True)
+        for _ in range(n_micro):
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                out = other(src, meta)
+            train.loss_fn(src, trg, out).backward()
+        torch.cuda.synchronize()
+        return {n: p.grad.clone() for n, p in other.named_parameters()}
+
+    g1, g2 = grads_after(1), grads_after(2)
+    for n in g1:
+        assert_close(g2[n], 2 * g1[n], 1e-5, 1e-6, what=f"accumulated gradient of {n}")
