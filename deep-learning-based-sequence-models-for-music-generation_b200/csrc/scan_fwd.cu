@@ -20,7 +20,7 @@
 //   * producer/consumer hand-off uses named barriers (bar.arrive / bar.sync), two per work slot.
 //   * every 16 timesteps the scan warps checkpoint h to HBM ([B, nck, N, D], coalesced) for the backward.
 //     deltaA / deltaB_u ([B, L, D, N] in the reference) never exist in memory.
-#include "common.cuh"
+#include "scan_fwd.cuh"
 
 namespace mb {
 
@@ -31,17 +31,6 @@ constexpr int kHelperThreads = kHelperWarps * 32;
 constexpr int kMaxScanWarps = 16;
 constexpr int kMaxBCVec = 4;  // precomputed B/C cp.async slots per helper thread (fast path)
 
-struct ScanFwdParams {
-  int B, L, D, N, N4, NS, NPT, nck, cki, flags;
-  const void *u, *delta, *Bm, *Cm, *z;
-  void* out;
-  int64_t u_bs, u_ls, delta_bs, delta_ls, B_bs, B_ls, C_bs, C_ls, z_bs, z_ls, out_bs, out_ls;
-  const float *A, *Dv, *dbias, *h_init;
-  float *ckpt, *h_last;
-  void* ypre;
-  int64_t ypre_bs, ypre_ls;
-  int vec_u, vec_delta, vec_z, vec_B, vec_C, vec_out, vec_ypre;
-};
 
 // 4 consecutive shared-memory elements as a float4 (bf16 widened in registers)
 __device__ __forceinline__ float4 ld4_as_f32(const float* p) { return *reinterpret_cast<const float4*>(p); }
@@ -487,9 +476,18 @@ extern "C" int mamba_scan_fwd(const MambaScanFwdArgs* a, void* stream) {
   p.ypre = a->y_pre, p.ypre_bs = a->y_pre_bs, p.ypre_ls = a->y_pre_ls;
   p.vec_ypre = a->y_pre ? vec_ok(a->y_pre, a->y_pre_bs, a->y_pre_ls, elt) : 0;
 
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // variant 100 + tune: the TMA-staged kernel (scan_fwd_tma.cu).  Automatic choice: d_state <= 32 takes it when the
+  // tensors can be described by tensor maps (config 5: 384 us against 529 us for this file's kernel at B=2, L=8192,
+  // N=16 fp32); at d_state 64 the two measure the same and this file's kernel stays the default.
+  if (a->variant >= 100 || (a->variant == 0 && p.N <= 32)) {
+    const int rc = launch_scan_fwd_tma(p, a->dtype, a->variant >= 100 ? a->variant - 100 : 0, st);
+    if (rc != kTmaNotEligible) return rc;
+    if (a->variant >= 100)
+      return set_error(MAMBA_EALIGN, "scan_fwd: variant %d (TMA) needs 16-byte aligned bases/strides and d_state <= 128", a->variant);
+  }
   int nper = a->variant;
   if (nper == 0) nper = p.N >= 64 ? 8 : 4;
   while (nper < 16 && ceil_div(p.N, nper) > kMaxScanWarps) nper *= 2;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   return a->dtype == MAMBA_F32 ? dispatch_nper<float>(p, nper, st) : dispatch_nper<__nv_bfloat16>(p, nper, st);
 }

@@ -76,7 +76,9 @@ typedef struct MambaScanFwdArgs {
   int32_t batch, seqlen, dim, dstate;
   int32_t chunk; /* checkpoint interval in timesteps: 8 or 16 (ignored if ckpt == NULL)     */
   int32_t flags;
-  int32_t variant; /* 0 = auto; otherwise states per thread (4, 8 or 16) — tuning knob */
+  int32_t variant; /* 0 = auto; 4, 8, 16 = LDGSTS-staged kernel with that many states per thread; 100 + 10*shape + split =
+                      TMA-staged kernel (shape 0 auto / 1 / 2 = tiling, split 0 / 1 = share of exp2 on the FMA pipe);
+                      tuning knob, results are the same within rounding */
   int32_t reserved;
   const void* u;     int64_t u_bs, u_ls;         /* [B, L, D]                 */
   const void* delta; int64_t delta_bs, delta_ls; /* [B, L, D] raw dt_proj out */

@@ -189,6 +189,65 @@ def test_scan_backward_variants_at_repo_d_state(variant, dtype, shape):
                      atol_abs=1e-6 if k == "A" else 0.0)
 
 
+# TMA-staged forward (scan_fwd_tma.cu): variant 100 + 10*tiling + split.  Shapes: 16-byte aligned rows (the kernel's
+# eligibility rule), ragged in L and in the channel tile, every d_state bracket (<=16, <=32, <=64, <=128).
+@pytest.mark.parametrize("variant", [110, 120, 111, 121])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(2, 7, 32, 16), (2, 333, 104, 16), (1, 130, 72, 32), (2, 100, 96, 64), (1, 49, 40, 128),
+                                   (1, 16, 32, 64), (2, 17, 64, 8)])
+def test_scan_forward_tma_variants_vs_oracle(variant, dtype, shape):
+    """Forward output, final state, and - through the checkpoints and y_pre this forward writes - every gradient of
+    the backward, for both tilings and both exp2 splits of the TMA-staged kernel."""
+    from mamba_b200 import ops
+    B, L, D, N = shape
+    if N > 64 and variant // 10 % 10 == 2:
+        pytest.skip("d_state > 64 has one tiling")
+    t = scan_inputs(B, L, D, N, seed=13, dtype=dtype)
+    dout = torch.randn(B, L, D, generator=torch.Generator().manual_seed(8)).to(dtype)
+    c = _leafs(t, "cpu")
+    ref, href = _oracle_scan(c, last_state=True)
+    ref.backward(dout.float())
+    g = _leafs(t, "cuda")
+    rtol, floor = (RTOL32, 1e-5) if dtype == torch.float32 else (RTOL16, FLOOR16)
+    ops.SCAN_FWD_VARIANT = variant
+    try:
+        for chunk in (8, 16):
+            for v in g.values():
+                v.grad = None
+            out = ops.selective_scan_fn(g["u"], g["delta_raw"], g["A"], g["B"], g["C"], g["D"], z=g["z"],
+                                        delta_bias=g["bias"], delta_softplus=True, chunk=chunk)
+            out.backward(dout.cuda())
+            assert_close(out, ref, rtol, floor, what=f"tma fwd {variant} {dtype} {shape}")
+            for k in c:
+                assert_close(g[k].grad, c[k].grad, rtol, floor, what=f"bwd after tma fwd {variant} {dtype} d{k} {shape} chunk {chunk}",
+                             atol_abs=1e-6 if k == "A" else 0.0)
+        with torch.no_grad():
+            out2, h = ops.selective_scan_prefill(g["u"], g["delta_raw"], g["A"], g["B"], g["C"], g["D"], z=g["z"],
+                                                 delta_bias=g["bias"], delta_softplus=True)
+        assert_close(out2, ref, rtol, floor, what=f"tma prefill {variant}")
+        assert_close(h, href, rtol, floor, what=f"tma last state {variant} {dtype} {shape}")
+    finally:
+        ops.SCAN_FWD_VARIANT = 0
+
+
+def test_scan_forward_tma_rejects_unaligned_rows_and_auto_falls_back():
+    """A forced TMA variant on rows that are not 16-byte multiples is an error (MAMBA_EALIGN); variant 0 silently uses
+    the LDGSTS kernel on the same problem and matches the oracle."""
+    from mamba_b200 import _lib, ops
+    t = scan_inputs(1, 40, 36, 5, seed=14)   # B/C rows of 5 floats = 20 bytes
+    g = {k: v.cuda() for k, v in t.items()}
+    ops.SCAN_FWD_VARIANT = 110
+    try:
+        with pytest.raises(_lib.MambaLibError, match="aligned"):
+            ops.selective_scan_fn(g["u"], g["delta_raw"], g["A"], g["B"], g["C"], g["D"], z=g["z"], delta_bias=g["bias"],
+                                  delta_softplus=True)
+    finally:
+        ops.SCAN_FWD_VARIANT = 0
+    out = ops.selective_scan_fn(g["u"], g["delta_raw"], g["A"], g["B"], g["C"], g["D"], z=g["z"], delta_bias=g["bias"],
+                                delta_softplus=True)
+    assert_close(out, _oracle_scan(t), RTOL32, what="auto fallback")
+
+
 def test_scan_state_carry_composes_at_full_size():
     """Size-independent property at BASELINE's long-context shape (L=8192, N=16, D=2048): scanning the whole
     sequence equals scanning two halves with the state carried (h_init), and equals the oracle on a slice."""
