@@ -14,7 +14,7 @@ EXPORTS = [
     "mamba_abi_version", "mamba_last_error", "mamba_launch_count",
     "mamba_scan_fwd", "mamba_scan_ckpt_elems", "mamba_scan_bwd", "mamba_scan_bwd_workspace_bytes",
     "mamba_conv1d_silu_fwd", "mamba_conv1d_silu_bwd", "mamba_conv1d_bwd_workspace_bytes",
-    "mamba_conv_step", "mamba_ssm_step", "mamba_linear_step",
+    "mamba_conv_step", "mamba_ssm_step", "mamba_linear_step", "mamba_fused_linear_step", "mamba_sample_step",
     "mamba_rmsnorm_fwd", "mamba_rmsnorm_bwd", "mamba_rmsnorm_bwd_workspace_bytes",
     "mamba_filtered_ce_fwd", "mamba_filtered_ce_bwd", "mamba_filtered_ce_workspace_bytes",
 ]
@@ -72,6 +72,24 @@ class LinearStepArgs(C.Structure):
                 ("out_features", i32), ("x", vp), ("x_bs", i64), ("weight", vp), ("bias", vp), ("y", vp), ("y_bs", i64)]
 
 
+class FusedLinearStepArgs(C.Structure):
+    _fields_ = [("struct_size", i32), ("dtype", i32), ("w_dtype", i32), ("batch", i32), ("in_features", i32),
+                ("out_features", i32), ("x", vp), ("x_bs", i64), ("weight", vp), ("bias", vp), ("y", vp), ("y_bs", i64),
+                ("norm_weight", fp), ("eps", C.c_float), ("conv_dim", i32),
+                ("residual_in", fp), ("residual_in_bs", i64), ("residual_out", fp), ("residual_out_bs", i64),
+                ("conv_width", i32), ("reserved", i32), ("conv_state", vp), ("conv_weight", fp), ("conv_bias", fp),
+                ("conv_out", vp), ("conv_out_bs", i64)]
+
+
+class SampleStepArgs(C.Structure):
+    _fields_ = [("struct_size", i32), ("mode", i32), ("batch", i32), ("vocab", i32), ("bucket_bounds", i32 * 4),
+                ("class_bounds", i32 * 4), ("pen_rule", i32 * 5), ("prompt_len", i32), ("time_budget", i32),
+                ("reserved", i32), ("pen_base", C.c_double * 5), ("pen_cap", C.c_double * 5),
+                ("logits", fp), ("logits_bs", i64), ("lse", fp), ("dist", fp), ("counts", vp),
+                ("generated", vp), ("generated_bs", i64), ("gen_len", vp), ("next_token", vp), ("uniforms", fp),
+                ("win_q", vp), ("win_sum", vp)]
+
+
 class LossArgs(C.Structure):
     _fields_ = [("struct_size", i32), ("dtype", i32), ("batch", i32), ("seqlen", i32), ("vocab", i32),
                 ("boundaries", i32 * 4), ("reserved", i32),
@@ -105,7 +123,8 @@ def lib() -> C.CDLL:
                        ("mamba_conv_step", StepArgs), ("mamba_ssm_step", StepArgs),
                        ("mamba_rmsnorm_fwd", NormArgs), ("mamba_rmsnorm_bwd", NormArgs),
                        ("mamba_filtered_ce_fwd", LossArgs), ("mamba_filtered_ce_bwd", LossArgs),
-                       ("mamba_linear_step", LinearStepArgs)):
+                       ("mamba_linear_step", LinearStepArgs), ("mamba_fused_linear_step", FusedLinearStepArgs),
+                       ("mamba_sample_step", SampleStepArgs)):
         f = getattr(L, name)
         f.restype = C.c_int
         f.argtypes = [C.POINTER(argt), C.c_void_p]
@@ -119,8 +138,8 @@ def lib() -> C.CDLL:
     L.mamba_filtered_ce_workspace_bytes.argtypes = [C.c_int] * 3
     L.mamba_rmsnorm_bwd_workspace_bytes.restype = sz
     L.mamba_rmsnorm_bwd_workspace_bytes.argtypes = [C.c_int64, C.c_int]
-    if L.mamba_abi_version() != 2:
-        raise MambaLibError(f"ABI version mismatch: library {L.mamba_abi_version()} != binding 2")
+    if L.mamba_abi_version() != 3:
+        raise MambaLibError(f"ABI version mismatch: library {L.mamba_abi_version()} != binding 3")
     _lib = L
     return L
 

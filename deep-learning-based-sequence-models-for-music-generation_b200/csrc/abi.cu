@@ -2,6 +2,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -25,6 +26,14 @@ int check_launch(const char* what) {
     return set_error(MAMBA_ELAUNCH, "%s: %s", what, cudaGetErrorString(e));
   }
   return MAMBA_OK;
+}
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("MAMBA_B200_PDL");   // opt-in: measured 7 % SLOWER on the decode chain (profiles/r02_decode.md)
+    return e && e[0] == '1';
+  }();
+  return on;
 }
 
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }

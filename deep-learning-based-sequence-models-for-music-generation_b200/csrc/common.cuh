@@ -204,6 +204,29 @@ __device__ __forceinline__ float colsum_32x8(const float* __restrict__ ws, int n
   return s;
 }
 
+// ---- programmatic dependent launch (decode chain) -----------------------------------------------------------------
+// The decode step is a chain of ~40 short kernels, each of which streams weights that do not depend on its
+// predecessor.  Launched with the programmatic-stream-serialization attribute, a kernel starts while the previous one
+// is still running: it signals its own dependents at once, prefetches its weights / state into L2, and only then
+// waits (griddepcontrol.wait) for the predecessor's results.  Everything before the wait must be independent of
+// earlier kernels of the chain.  In a kernel launched without the attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+bool pdl_enabled();  // abi.cu: MAMBA_B200_PDL == "1" (off by default)
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_chain(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
 __host__ __device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }

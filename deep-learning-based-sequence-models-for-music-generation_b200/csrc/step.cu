@@ -88,6 +88,9 @@ template <typename T>
 __global__ void __launch_bounds__(256) ssm_step_fast_kernel(const StepParams p) {
   const int hl = threadIdx.x & 15;
   const int64_t item = (int64_t)blockIdx.x * (blockDim.x >> 4) + (threadIdx.x >> 4);
+  pdl_launch_dependents();  // decode chain (common.cuh)
+  if (item < (int64_t)p.B * p.D && hl < 2) prefetch_l2(p.h + item * p.N + hl * 32);  // this pair's state row (<= 256 B)
+  pdl_wait();
   if (item >= (int64_t)p.B * p.D) return;  // whole half-warps leave together; shuffles below use per-half masks
   const unsigned mask = 0xffffu << (threadIdx.x & 16);
   const int b = (int)(item / p.D), d = (int)(item - (int64_t)b * p.D);
@@ -191,9 +194,9 @@ extern "C" int mamba_ssm_step(const MambaStepArgs* a, void* stream) {
     const int64_t items = (int64_t)p.B * p.D;
     const int blocks = (int)((items + 15) / 16);
     if (a->dtype == MAMBA_F32)
-      ssm_step_fast_kernel<float><<<blocks, 256, 0, st>>>(p);
+      launch_chain(ssm_step_fast_kernel<float>, dim3(blocks), dim3(256), 0, st, p);
     else
-      ssm_step_fast_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(p);
+      launch_chain(ssm_step_fast_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, st, p);
   } else {
     const int warps = 8;
     const int blocks = ceil_div(p.D, warps);

@@ -14,7 +14,7 @@ from __future__ import annotations
 
 import torch
 
-from . import train
+from . import ops, train
 from .configs import common as cc
 
 
@@ -68,66 +68,93 @@ def generate_literal(model, context_len, token_ids, meta_ids, num_tokens=1000):
 
 
 class RecurrentDecoder:
-    """Prefill + CUDA-graphed single-token step for a fixed batch size."""
+    """Prefill + CUDA-graphed single-token step for a fixed batch of independent sequences.
 
-    def __init__(self, model, batch_size, use_graph=True, dtype=None):
+    One step = embedding lookup, 4 launches per layer (`Mamba.step`'s fused path), the head with the final norm
+    folded in, and ONE launch of `mamba_sample_step` that applies filtered_logit, the repetition penalties, picks
+    the token, appends it to `generated` and advances the look-back window (csrc/sample.cu).
+    mode "many":   greedy, scripts/generate_midi_many.py:13-56.
+    mode "sample": top-k draw of scripts/generate.py:14-95; `uniforms` [max_new, B, 2] supplies the randomness
+                   (default: torch.rand from `generator`, i.e. a Philox stream with a fixed seed)."""
+
+    def __init__(self, model, batch_size, use_graph=True, dtype=None, mode="many", max_new_tokens=4096, uniforms=None,
+                 generator=None):
+        if mode not in ("many", "sample"):
+            raise ValueError("mode must be 'many' or 'sample'")
         self.model = model.eval()
         self.B = batch_size
+        self.mode = 0 if mode == "many" else 1
         self.dev = next(model.parameters()).device
         self.cache = model.allocate_inference_cache(batch_size, dtype=dtype)
-        self.table = _penalty_table_many(self.dev)
         V = cc.vocab_size
-        self.lse = torch.zeros(batch_size, V, device=self.dev)            # running logsumexp over positions
-        self.counts = torch.zeros(batch_size, V, device=self.dev)         # occurrences in the last 100 tokens
-        self.window = torch.zeros(batch_size, 100, dtype=torch.long, device=self.dev)
-        self.wfill = 0
-        self.cur = torch.zeros(batch_size, dtype=torch.long, device=self.dev)   # last token (input of the step)
+        self.max_new = int(max_new_tokens)
+        self.lse = torch.zeros(batch_size, V, device=self.dev)                      # running logsumexp over positions
+        self.counts = torch.zeros(batch_size, V, dtype=torch.int32, device=self.dev)  # occurrences in the window
+        self.logits = torch.zeros(batch_size, V, device=self.dev)
         self.nxt = torch.zeros(batch_size, dtype=torch.long, device=self.dev)
+        self.gen_len = torch.zeros(batch_size, dtype=torch.int32, device=self.dev)
+        self.win_q = torch.zeros(batch_size, dtype=torch.int32, device=self.dev)
+        self.win_sum = torch.zeros(batch_size, dtype=torch.int32, device=self.dev)
+        self.generated = None
+        self.uniforms = uniforms
+        self.generator = generator
+        self.dist = train.make_distributions(self.dev).contiguous()
         self.use_graph = use_graph
         self.graph = None
+        self.sargs = None
 
     @torch.no_grad()
     def prefill(self, token_ids, meta_ids):
+        B, T = token_ids.shape
+        s = cc.start_idx
         logits = self.model.prefill(token_ids, meta_ids, self.cache).float()      # [B, T, V]
-        self.lse.copy_(torch.logsumexp(logits, dim=1))
-        recent = token_ids[:, -100:]
-        self.counts.zero_().scatter_add_(1, recent, torch.ones_like(recent, dtype=torch.float32))
-        n = recent.shape[1]
-        self.window.zero_()
-        self.window[:, 100 - n:] = recent
-        self.wfill = n
-        self._choose(logits[:, -1, :], token_ids[:, -1])
+        # sequence-axis logsumexp over the positions BEFORE the last one; the sample kernel adds the last
+        if T > 1:
+            self.lse.copy_(torch.logsumexp(logits[:, :-1], dim=1))
+        else:
+            self.lse.fill_(float("-inf"))
+        self.logits.copy_(logits[:, -1])
+        self.generated = torch.zeros(B, T + self.max_new + 1, dtype=torch.long, device=self.dev)
+        self.generated[:, :T] = token_ids
+        self.gen_len.fill_(T)
+        # look-back window over the prompt (host side, once): counts of the tokens inside it
+        toks = token_ids.cpu()
+        counts = torch.zeros(B, cc.vocab_size, dtype=torch.int32)
+        q0 = torch.zeros(B, dtype=torch.int32)
+        sum0 = torch.zeros(B, dtype=torch.int32)
+        for b in range(B):
+            row = toks[b].tolist()
+            if self.mode == 0:
+                win = row[-100:]
+            else:
+                tv = [t - s["time"] if s["time"] <= t < s["tempo"] else 0 for t in row]
+                q, tot = 0, sum(tv)
+                while q < T - 1 and tot - tv[q] >= 64 * 16:
+                    tot -= tv[q]
+                    q += 1
+                q0[b], sum0[b] = q, tot
+                win = row[q + 1:] if T > 1 else row     # scripts/generate.py:38-46 (`cur_gen[-0:]` is the whole list)
+            for t in win:
+                counts[b, t] += 1
+        self.counts.copy_(counts)
+        self.win_q.copy_(q0)
+        self.win_sum.copy_(sum0)
+        if self.mode == 1 and self.uniforms is None:
+            self.uniforms = torch.rand(self.max_new + 1, B, 2, device=self.dev, generator=self.generator)
+        self.sargs = ops.sample_step_args(
+            self.mode, self.logits, self.lse, self.dist, self.counts, self.generated, self.gen_len, self.nxt,
+            (s["dyn"], s["length"], s["time"], s["tempo"]), T, uniforms=self.uniforms, win_q=self.win_q, win_sum=self.win_sum)
+        ops.sample_step(self.sargs, self.dev)
         return self.nxt.clone()
 
-    def _choose(self, logits_last, prev_token):
-        """filtered_logit at the last position + penalties + argmax (generate_midi_many.py:20-46)."""
-        weights = train.pick_distributions_by_prev_token(prev_token)             # [B, V]
-        f = -(logits_last - self.lse) * weights
-        f = _apply_penalty_many(f, self.counts, self.table)
-        self.nxt.copy_(f.argmax(-1))
-
-    def _slide(self, tok):
-        """Push `tok` into the 100-token look-back window and keep `counts` in step."""
-        full = self.wfill >= 100
-        if full:
-            old = self.window[:, 0:1]
-            self.counts.scatter_add_(1, old, -torch.ones_like(old, dtype=torch.float32))
-        self.window.copy_(torch.cat((self.window[:, 1:], tok[:, None]), dim=1))
-        self.counts.scatter_add_(1, tok[:, None], torch.ones(self.B, 1, device=self.dev))
-        if not full:
-            self.wfill += 1
-
     def _step_body(self):
-        self.cur.copy_(self.nxt)
-        self._slide(self.cur)
-        logits = self.model.step(self.cur, self.cache).float()
-        self.lse.copy_(torch.logaddexp(self.lse, logits))
-        self._choose(logits, self.cur)
+        self.model.step(self.nxt, self.cache, logits_out=self.logits)
+        ops.sample_step(self.sargs, self.dev)
 
     @torch.no_grad()
     def step(self):
         """Consume the previously chosen token, produce the next one (device tensor [B])."""
-        if self.use_graph and self.wfill >= 100:
+        if self.use_graph:
             if self.graph is None:
                 s = torch.cuda.Stream(device=self.dev)
                 s.wait_stream(torch.cuda.current_stream(self.dev))
@@ -136,6 +163,8 @@ class RecurrentDecoder:
                     self._step_body()
                 torch.cuda.current_stream(self.dev).wait_stream(s)
                 torch.cuda.synchronize(self.dev)
+                self._restore(saved)
+                saved = self._snapshot()
                 self.graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(self.graph):
                     self._step_body()
@@ -145,8 +174,13 @@ class RecurrentDecoder:
             self._step_body()
         return self.nxt
 
+    def tokens(self):
+        """[B, prompt + generated so far] (all rows have the same length)."""
+        n = int(self.gen_len[0])
+        return self.generated[:, :n].clone()
+
     def _state_tensors(self):
-        ts = [self.lse, self.counts, self.window, self.cur, self.nxt]
+        ts = [self.lse, self.counts, self.logits, self.nxt, self.gen_len, self.win_q, self.win_sum, self.generated]
         for cs, hs in self.cache:
             ts += [cs, hs]
         return ts
@@ -160,11 +194,24 @@ class RecurrentDecoder:
 
 
 @torch.no_grad()
-def generate_recurrent(model, token_ids, meta_ids, num_tokens=1000, use_graph=True, dtype=None):
-    """Greedy decode of `num_tokens` new tokens for each row of token_ids; returns [B, T + num_tokens]."""
-    dec = RecurrentDecoder(model, token_ids.shape[0], use_graph=use_graph, dtype=dtype)
-    out = torch.empty(token_ids.shape[0], num_tokens, dtype=torch.long, device=token_ids.device)
-    out[:, 0] = dec.prefill(token_ids, meta_ids)
-    for i in range(1, num_tokens):
-        out[:, i] = dec.step()
-    return torch.cat((token_ids, out), dim=1)
+def generate_recurrent(model, token_ids, meta_ids, num_tokens=1000, use_graph=True, dtype=None, mode="many",
+                       uniforms=None, generator=None):
+    """`num_tokens` new tokens for each row of token_ids; returns [B, T + num_tokens].  mode "many": greedy
+    (scripts/generate_midi_many.py); mode "sample": the top-k draw of scripts/generate.py with the given uniforms."""
+    dec = RecurrentDecoder(model, token_ids.shape[0], use_graph=use_graph, dtype=dtype, mode=mode,
+                           max_new_tokens=num_tokens, uniforms=uniforms, generator=generator)
+    dec.prefill(token_ids, meta_ids)
+    for _ in range(1, num_tokens):
+        dec.step()
+    return dec.tokens()
+
+
+def generate(model, context_len, token_ids, meta_ids, num_tokens=1000, device="cuda", seed=None):
+    """Drop-in for scripts/generate.py:14-95 (same arguments, returns a list of token lists): recurrent decode with
+    the on-device sampler.  The window never slides (state is carried), so `context_len` only bounds the prompt."""
+    token_ids, meta_ids = token_ids.to(device), meta_ids.to(device)
+    gen = None
+    if seed is not None:
+        gen = torch.Generator(device=token_ids.device).manual_seed(int(seed))
+    out = generate_recurrent(model, token_ids[:, -context_len:], meta_ids, num_tokens, mode="sample", generator=gen)
+    return [row.tolist() for row in out.cpu()]

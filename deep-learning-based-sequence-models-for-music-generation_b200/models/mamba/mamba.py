@@ -322,6 +322,24 @@ class MambaBlock(nn.Module):  # simple_mamba @L184
         return _linear_step(y, self.out_proj)
 
 
+    @torch.no_grad()
+    def step_fused(self, hidden, resid_in, resid_out, norm, conv_state, ssm_state, k):
+        """One new position through `norm -> mixer` of the residual block in FOUR launches (decode, <= 16 sequences):
+        in_proj with the block's RMSNorm + residual add as its prologue and the conv step as its epilogue, x_proj,
+        the SSM step (dt_proj + softplus + recurrence + D skip + gate), out_proj.
+        hidden: previous mixer output [B, d_model] or None (first layer); resid_in / resid_out: fp32 residual stream
+        (ping-pong buffers).  Returns the mixer output [B, d_model]."""
+        p = self.params
+        xz, xc = ops.fused_linear_step(hidden, self.in_proj.weight.detach(), None if self.in_proj.bias is None else self.in_proj.bias.detach(),
+                                       norm_weight=k["norm_w"], eps=norm.eps, residual_in=resid_in, residual_out=resid_out,
+                                       conv_state=conv_state, conv_weight=k["conv_w"], conv_bias=k["conv_b"])
+        res = xz[:, p.d_inner:]
+        x_dbl = ops.linear_step(xc, self.x_proj.weight.detach(), None)
+        dt_r, Bv, Cv = x_dbl.split([p.dt_rank, p.d_state, p.d_state], dim=-1)
+        y = ops.ssm_step(xc, dt_r, Bv, Cv, k["dt_w"], k["dt_b"], k["A"], k["D"], res, ssm_state)
+        return ops.linear_step(y, self.out_proj.weight.detach(), None if self.out_proj.bias is None else self.out_proj.bias.detach())
+
+
 class ResidualBlock(nn.Module):  # simple_mamba @L151-181
     def __init__(self, params, layer_idx=None):
         super().__init__()
@@ -473,8 +491,10 @@ class Mamba(nn.Module):
         return self._head(normed[:, n_meta:])
 
     @torch.no_grad()
-    def step(self, token, cache):
-        """token [B] long -> logits [B, V]; advances every layer's state by one position."""
+    def step(self, token, cache, logits_out=None):
+        """token [B] long -> logits [B, V]; advances every layer's state by one position.  Layout P on CUDA with
+        <= 16 sequences takes the fused path (4 launches per layer, norm and conv folded into in_proj; the final
+        norm folded into the head); `logits_out` (fp32 [B, V]) receives the logits when given."""
         tok = self.embedding if self.layout == "P" else self.token_embedding
         mixers = [l.mixer if self.layout == "P" else l for l in self.layers]
         consts = getattr(cache, "consts", None)
@@ -484,6 +504,9 @@ class Mamba(nn.Module):
                 cache.consts = consts
             except AttributeError:  # a plain list was passed: rebuilt per call
                 pass
+        if (self.layout == "P" and token.is_cuda and token.shape[0] <= 16 and self.params.d_model % 4 == 0
+                and getattr(cache, "fused", True)):
+            return self._step_fused(tok, token, mixers, cache, consts, logits_out)
         x = tok(token)
         if self.layout == "S":
             for layer, (cs, hs), k in zip(self.layers, cache, consts):
@@ -494,4 +517,29 @@ class Mamba(nn.Module):
             normed, resid = layer.norm(hidden, resid)
             hidden = layer.mixer.step(normed, cs, hs, k)
         normed, _ = self.norm_f(hidden, resid)
-        return _linear_step(normed, self.lm_head)
+        out = _linear_step(normed, self.lm_head)
+        if logits_out is not None:
+            logits_out.copy_(out)
+            return logits_out
+        return out
+
+    def _step_fused(self, tok, token, mixers, cache, consts, logits_out):
+        B = token.shape[0]
+        dev = token.device
+        for layer, k in zip(self.layers, consts):
+            if "norm_w" not in k:
+                k["norm_w"] = layer.norm.weight.detach().float().contiguous()
+        resid = tok(token).float()                       # residual stream, fp32 (as Mamba.forward keeps it)
+        spare = torch.empty_like(resid)
+        hidden = None
+        for layer, (cs, hs), k in zip(self.layers, cache, consts):
+            hidden = layer.mixer.step_fused(hidden, resid, spare, layer.norm, cs, hs, k)
+            resid, spare = spare, resid
+        w = self.lm_head.weight.detach()
+        out = ops.fused_linear_step(hidden, w, None if self.lm_head.bias is None else self.lm_head.bias.detach(),
+                                    norm_weight=self.norm_f.weight.detach().float(), eps=self.norm_f.eps, residual_in=resid,
+                                    out=logits_out if (logits_out is not None and logits_out.dtype == hidden.dtype) else None)
+        if logits_out is not None and out is not logits_out:
+            logits_out.copy_(out)
+            return logits_out
+        return out

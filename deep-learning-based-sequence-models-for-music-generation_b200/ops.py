@@ -19,7 +19,7 @@ import torch
 
 from . import _lib
 from ._lib import (FLAG_A_IS_LOG, FLAG_DELTA_SOFTPLUS, FLAG_HAS_D, FLAG_HAS_DELTA_BIAS, FLAG_HAS_Z, MAMBA_BF16, MAMBA_F32, ConvArgs,
-                   LinearStepArgs, LossArgs, NormArgs, ScanBwdArgs, ScanFwdArgs, StepArgs, check, lib)
+                   FusedLinearStepArgs, LinearStepArgs, SampleStepArgs, LossArgs, NormArgs, ScanBwdArgs, ScanFwdArgs, StepArgs, check, lib)
 
 _DTYPES = {torch.float32: MAMBA_F32, torch.bfloat16: MAMBA_BF16}
 
@@ -605,6 +605,89 @@ def linear_step(x, weight, bias=None):
     a.y, a.y_bs = _p(y), y.stride(0)
     _call("mamba_linear_step", a, x.device)
     return y
+
+
+def fused_linear_step(x, weight, bias=None, *, norm_weight=None, eps=1e-5, residual_in=None, residual_out=None,
+                      conv_state=None, conv_weight=None, conv_bias=None, out=None):
+    """linear_step with the residual block's per-token neighbours folded in (decode; include/mamba_b200.h
+    mamba_fused_linear_step): optional prologue x := rmsnorm(x + residual_in) * norm_weight (residual_out receives the
+    sum; x may be None), optional epilogue on the first conv_state.shape[1] output columns (depthwise conv step + SiLU,
+    conv_state updated in place).  Returns y, or (y, conv_out) with an epilogue."""
+    _require_cuda(x, weight, bias, norm_weight, residual_in, residual_out, conv_state, conv_weight, conv_bias)
+    ref = x if x is not None else residual_in
+    Bsz, K = ref.shape
+    N = weight.shape[0]
+    if weight.shape[1] != K or not weight.is_contiguous():
+        raise ValueError("fused_linear_step: weight must be contiguous [N, K]")
+    if x is not None and x.stride(-1) != 1:
+        raise ValueError("fused_linear_step: x must have unit inner stride")
+    if bias is not None and bias.dtype != weight.dtype:
+        bias = bias.to(weight.dtype)
+    act = x.dtype if x is not None else (conv_state.dtype if conv_state is not None else weight.dtype)
+    y = out if out is not None else torch.empty((Bsz, N), dtype=act, device=ref.device)
+    a = FusedLinearStepArgs()
+    a.struct_size = ct.sizeof(FusedLinearStepArgs)
+    a.dtype, a.w_dtype = _DTYPES[act], _dtype_code(weight)
+    a.batch, a.in_features, a.out_features = Bsz, K, N
+    if x is not None:
+        a.x, a.x_bs = _p(x), x.stride(0)
+    a.weight, a.bias = _p(weight), _p(bias)
+    a.y, a.y_bs = _p(y), y.stride(0)
+    if norm_weight is not None:
+        if norm_weight.dtype != torch.float32 or (residual_in is not None and residual_in.dtype != torch.float32) or (
+                residual_out is not None and residual_out.dtype != torch.float32):
+            raise TypeError("fused_linear_step: norm weight and the residual stream are fp32")
+        a.norm_weight, a.eps = _p(norm_weight), float(eps)
+        if residual_in is not None:
+            a.residual_in, a.residual_in_bs = _p(residual_in), residual_in.stride(0)
+        if residual_out is not None:
+            a.residual_out, a.residual_out_bs = _p(residual_out), residual_out.stride(0)
+    conv_out = None
+    if conv_state is not None:
+        Dc, Kc = conv_state.shape[1], conv_state.shape[2]
+        if conv_state.dtype != act or not conv_state.is_contiguous():
+            raise ValueError("fused_linear_step: conv_state must be contiguous and of the activation dtype")
+        conv_out = torch.empty((Bsz, Dc), dtype=act, device=ref.device)
+        a.conv_dim, a.conv_width = Dc, Kc
+        a.conv_state, a.conv_weight, a.conv_bias = _p(conv_state), _p(conv_weight), _p(conv_bias)
+        a.conv_out, a.conv_out_bs = _p(conv_out), conv_out.stride(0)
+    _call("mamba_fused_linear_step", a, ref.device)
+    return y if conv_state is None else (y, conv_out)
+
+
+def sample_step_args(mode, logits, lse, dist, counts, generated, gen_len, next_token, bounds, prompt_len, uniforms=None,
+                     win_q=None, win_sum=None):
+    """Fill a MambaSampleStepArgs (reused across steps by the decoder; every pointer is a persistent buffer).
+    bounds = (dyn, length, time, tempo) first-token ids."""
+    _require_cuda(logits, lse, dist, counts, generated, gen_len, next_token, uniforms, win_q, win_sum)
+    if logits.dtype != torch.float32 or lse.dtype != torch.float32 or dist.dtype != torch.float32:
+        raise TypeError("sample_step: logits, lse and dist are fp32")
+    if counts.dtype != torch.int32 or gen_len.dtype != torch.int32 or generated.dtype != torch.int64 or next_token.dtype != torch.int64:
+        raise TypeError("sample_step: counts/gen_len int32, generated/next_token int64")
+    a = SampleStepArgs()
+    a.struct_size = ct.sizeof(SampleStepArgs)
+    a.mode, a.batch, a.vocab = int(mode), logits.shape[0], logits.shape[1]
+    dyn, length, time, tempo = (int(v) for v in bounds)
+    a.bucket_bounds = (ct.c_int32 * 4)(dyn - 1, length - 1, time - 1, tempo - 1)
+    a.class_bounds = (ct.c_int32 * 4)(dyn, length, time, tempo)
+    if mode == 0:   # scripts/generate_midi_many.py:24-43
+        rule, base, cap = (1, 0, 1, 2, 0), (1.04, 1.0, 1.015, 1.0, 1.0), (1.25, 1.0, 1.08, 1.0, 1.0)
+    else:           # scripts/generate.py:60-71
+        rule, base, cap = (1, 1, 0, 0, 0), (1.01, 1.02, 1.0, 1.0, 1.0), (1.2, 1.2, 1.0, 1.0, 1.0)
+    a.pen_rule = (ct.c_int32 * 5)(*rule)
+    a.pen_base = (ct.c_double * 5)(*base)
+    a.pen_cap = (ct.c_double * 5)(*cap)
+    a.prompt_len, a.time_budget = int(prompt_len), 64 * 16
+    a.logits, a.logits_bs = _p(logits), logits.stride(0)
+    a.lse, a.dist, a.counts = _p(lse), _p(dist), _p(counts)
+    a.generated, a.generated_bs = _p(generated), generated.stride(0)
+    a.gen_len, a.next_token = _p(gen_len), _p(next_token)
+    a.uniforms, a.win_q, a.win_sum = _p(uniforms), _p(win_q), _p(win_sum)
+    return a
+
+
+def sample_step(args, device):
+    _call("mamba_sample_step", args, device)
 
 
 def launch_count() -> int:

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define MAMBA_ABI_VERSION 2
+#define MAMBA_ABI_VERSION 3
 
 enum { MAMBA_F32 = 0, MAMBA_BF16 = 1 };
 
@@ -232,6 +232,78 @@ typedef struct MambaLinearStepArgs {
 } MambaLinearStepArgs;
 
 int mamba_linear_step(const MambaLinearStepArgs* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * mamba_linear_step with the neighbouring per-token work of the residual block folded in (decode only):
+ *   prologue (norm_weight != NULL):  s = x + residual_in  (x NULL = zeros; fp32 residual stream);
+ *                                    residual_out = s;  x' = s * rsqrt(mean(s^2) + eps) * norm_weight
+ *                                    — `normed, resid = norm(hidden, resid)` of ResidualBlock.forward
+ *                                    (simple_mamba.pyc @L179 with RMSNorm @L346) in front of in_proj @L230 / lm_head @L94;
+ *   epilogue (conv_dim > 0):         output columns [0, conv_dim) are the conv branch of in_proj: each value is pushed
+ *                                    into conv_state[b, n, :] (shift register of `conv_width` taps) and
+ *                                    conv_out[b, n] = silu(conv_bias[n] + sum_k conv_weight[n, k] * conv_state[b, n, k])
+ *                                    (@L233-237 for one new position: mamba_conv_step); the remaining columns
+ *                                    (the gate z) go to y as usual.
+ * residual_out must not alias residual_in.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct MambaFusedLinearStepArgs {
+  int32_t struct_size;
+  int32_t dtype, w_dtype;
+  int32_t batch, in_features, out_features;
+  const void* x;      int64_t x_bs;   /* [B, in_features] or NULL (with a fused norm)  */
+  const void* weight;                 /* [out_features, in_features] contiguous */
+  const void* bias;                   /* [out_features] or NULL */
+  void* y;            int64_t y_bs;   /* [B, out_features] */
+  const float* norm_weight;           /* [in_features] or NULL (no prologue) */
+  float eps;
+  int32_t conv_dim;                   /* 0 = no epilogue */
+  const float* residual_in;  int64_t residual_in_bs;   /* [B, in_features] fp32 or NULL */
+  float* residual_out;       int64_t residual_out_bs;  /* [B, in_features] fp32 or NULL */
+  int32_t conv_width, reserved;
+  void* conv_state;                   /* [B, conv_dim, conv_width], activation dtype, updated in place */
+  const float* conv_weight;           /* [conv_dim, conv_width] */
+  const float* conv_bias;             /* [conv_dim] or NULL */
+  void* conv_out;     int64_t conv_out_bs;  /* [B, conv_dim] */
+} MambaFusedLinearStepArgs;
+
+int mamba_fused_linear_step(const MambaFusedLinearStepArgs* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Next-token choice for one decode step, one CTA per sequence (csrc/sample.cu).  Replaces the per-token host code of
+ *   mode 0: scripts/generate_midi_many.py:20-46  (filtered_logit at the last position, penalties over the last 100
+ *           tokens, argmax), and
+ *   mode 1: scripts/generate.py:33-85  (filtered_logit, penalties over the time-bounded look-back window, k drawn by
+ *           the class of the last token, top-k, one draw from the k values normalised by their sum),
+ * including the bookkeeping: the chosen token is appended to `generated`, `gen_len` is advanced and `counts` (the
+ * occurrences of every token inside the look-back window) is kept in step.  train.filtered_logit's SEQUENCE-axis
+ * log_softmax (train.py:133-138) is carried as a running logsumexp per (sequence, token): lse <- logaddexp(lse, logits).
+ * Randomness (mode 1) is supplied by the caller: uniforms[step][b][0] picks k, uniforms[step][b][1] is the draw
+ * (inverse CDF), step = gen_len[b] - prompt_len.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct MambaSampleStepArgs {
+  int32_t struct_size;
+  int32_t mode;
+  int32_t batch, vocab;
+  int32_t bucket_bounds[4]; /* {dyn-1, length-1, time-1, tempo-1}: torch.bucketize boundaries of train.py:114-131 */
+  int32_t class_bounds[4];  /* {dyn, length, time, tempo}: first token id of each class after pitch             */
+  int32_t pen_rule[5];      /* per token class: 0 none, 1 min(base**count, cap), 2 (1.1*count if count >= 10)    */
+  int32_t prompt_len;
+  int32_t time_budget;      /* mode 1: 64*16 (scripts/generate.py:43) */
+  int32_t reserved;
+  double pen_base[5], pen_cap[5];
+  const float* logits;  int64_t logits_bs;   /* [B, V] fp32: the model's output for the last position */
+  float* lse;               /* [B, V] running logsumexp over the positions seen so far (updated) */
+  const float* dist;        /* [5, V] weights of train.make_distributions (train.py:79-111)     */
+  int32_t* counts;          /* [B, V] occurrences inside the look-back window (updated)         */
+  int64_t* generated;   int64_t generated_bs; /* [B, capacity] token ids (appended)             */
+  int32_t* gen_len;         /* [B] number of valid entries of `generated` (advanced)            */
+  int64_t* next_token;      /* [B] the chosen token                                             */
+  const float* uniforms;    /* mode 1: [steps, B, 2] uniforms in [0, 1)                          */
+  int32_t* win_q;           /* mode 1: [B] left edge of the look-back window (updated)           */
+  int32_t* win_sum;         /* mode 1: [B] sum of time shifts over generated[win_q:] (updated)   */
+} MambaSampleStepArgs;
+
+int mamba_sample_step(const MambaSampleStepArgs* args, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * RMSNorm with fused residual add.  Replaces RMSNorm.forward (simple_mamba.pyc @L346) and the

@@ -113,3 +113,76 @@ def generate_greedy(model, context_len, token_ids, meta_ids, num_tokens, disc=DI
             token_ids = torch.cat([token_ids, next_token], dim=1)
             token_ids = token_ids[:, -context_len:]
     return generated
+
+
+def choose_sampling(logits_last_row, cur_gen, u0, u1, start_idx):
+    """One row of scripts/generate.py:33-85 — look-back window, k, penalties, top-k, one draw — with the two random
+    numbers injected: `random.choice(seq)` is seq[int(u0 * len(seq))] and `torch.multinomial(p, 1)` is the inverse CDF
+    of p at u1 (the library calls consume their generators differently; identical uniforms -> identical tokens is the
+    parity definition for this path).  logits_last_row: 1-D tensor, modified in place as the script does."""
+    val = 0
+    j = 0
+    for j, token in enumerate(reversed(cur_gen)):                      # :38-44
+        if start_idx["time"] <= token < start_idx["tempo"]:
+            val += token - start_idx["time"]
+        if val >= 64 * 16:
+            break
+    recent = cur_gen[-j:]                                              # :45-46 (j == 0: the whole list)
+
+    def choice(seq):
+        return seq[min(int(u0 * len(seq)), len(seq) - 1)]
+
+    k = 1
+    if start_idx["tempo"] <= cur_gen[-1]:                              # :48-58
+        k = choice([1, 1, 1, 2, 2])
+    elif start_idx["time"] <= cur_gen[-1]:
+        pass
+    elif start_idx["length"] <= cur_gen[-1]:
+        pass
+    elif start_idx["dyn"] <= cur_gen[-1]:
+        k = choice([1, 3])
+    else:
+        k = choice([1, 2])
+    for token, count in Counter(recent).items():                       # :60-73
+        if start_idx["tempo"] <= token:
+            continue
+        elif start_idx["time"] <= token:
+            continue
+        elif start_idx["length"] <= token:
+            continue
+        elif start_idx["dyn"] <= token:
+            penalty = min(1.02 ** count, 1.2)
+        else:
+            penalty = min(1.01 ** count, 1.2)
+        if count > 0:
+            logits_last_row[token] /= penalty
+    topk_probs, topk_indices = torch.topk(logits_last_row, k)          # :78-81
+    topk_probs = topk_probs / topk_probs.sum()
+    acc, pick = 0.0, k - 1
+    acc = torch.zeros((), dtype=topk_probs.dtype)
+    for jj in range(k):
+        acc = acc + topk_probs[jj]
+        if u1 < float(acc):
+            pick = jj
+            break
+    return int(topk_indices[pick])
+
+
+def generate_sampling(model, context_len, token_ids, meta_ids, num_tokens, uniforms, disc=DISCRETIZATION):
+    """scripts/generate.py:14-95 with injected uniforms [num_tokens, B, 2] (see choose_sampling)."""
+    _, start_idx = vocab_layout(disc)
+    model.eval()
+    gen = [row.tolist() for row in token_ids.cpu()]
+    with torch.no_grad():
+        for step in range(num_tokens):
+            if token_ids.size(1) > context_len:
+                token_ids = token_ids[:, -context_len:]
+            logits = model(token_ids, meta_ids)
+            logits_last = filtered_logit(token_ids, logits, disc)[:, -1, :]
+            nxt = []
+            for i in range(len(gen)):
+                tok = choose_sampling(logits_last[i], gen[i], float(uniforms[step, i, 0]), float(uniforms[step, i, 1]), start_idx)
+                gen[i].append(tok)
+                nxt.append(tok)
+            token_ids = torch.cat([token_ids, torch.tensor(nxt, device=token_ids.device).unsqueeze(1)], dim=1)
+    return gen

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol(lib):
     for name in _declared_functions():
         assert hasattr(lib, name), f"libmamba_b200.so does not export {name}"
     assert set(_lib.EXPORTS) == set(_declared_functions())
-    assert lib.mamba_abi_version() == 2
+    assert lib.mamba_abi_version() == 3
 
 
 def test_ctypes_struct_layout_matches_c(tmp_path):
@@ -38,7 +38,8 @@ def test_ctypes_struct_layout_matches_c(tmp_path):
     from mamba_b200 import _lib
     structs = {"MambaScanFwdArgs": _lib.ScanFwdArgs, "MambaScanBwdArgs": _lib.ScanBwdArgs,
                "MambaConvArgs": _lib.ConvArgs, "MambaStepArgs": _lib.StepArgs, "MambaNormArgs": _lib.NormArgs,
-               "MambaLossArgs": _lib.LossArgs, "MambaLinearStepArgs": _lib.LinearStepArgs}
+               "MambaLossArgs": _lib.LossArgs, "MambaLinearStepArgs": _lib.LinearStepArgs,
+               "MambaFusedLinearStepArgs": _lib.FusedLinearStepArgs, "MambaSampleStepArgs": _lib.SampleStepArgs}
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void){"]
     for cname, ct in structs.items():
         lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')

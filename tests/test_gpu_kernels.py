@@ -623,3 +623,115 @@ def test_scan_with_A_given_as_A_log(shape, dtype):
     assert_close(g_Alog.grad, c_Alog.grad, rtol, floor, what=f"scan bwd dA_log {shape}", atol_abs=1e-6)
     for k in ("u", "delta_raw", "B", "C", "D", "z", "bias"):
         assert_close(g[k].grad, c[k].grad, rtol, floor, what=f"scan bwd (A_log) d{k} {shape}")
+
+
+# ---- on-device sampler (csrc/sample.cu) ---------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", [0, 1])
+def test_sample_step_kernel_vs_python_restatement(mode):
+    """mamba_sample_step over 260 steps of synthetic logits against the reference loops restated in python
+    (mode 0: scripts/generate_midi_many.py:20-46 via the oracle's penalties; mode 1: scripts/generate.py:33-85 via
+    oracle.train_ref.choose_sampling).  Every step the python side recomputes the choice in float64 from the kernel's
+    own running logsumexp; a different token is accepted only as a numerical tie (top candidates within 1e-5
+    relative) and the python history then follows the kernel, so the window / count bookkeeping stays comparable:
+    `counts` must equal Counter(window) exactly at every check."""
+    from collections import Counter
+    from mamba_b200 import ops
+    from mamba_b200.configs import common as cc
+    from oracle import train_ref
+    V, s = cc.vocab_size, cc.start_idx
+    B, T0, steps = 4, 150, 260
+    g = torch.Generator().manual_seed(21 + mode)
+    # prompts rich in time-shift tokens so that the time-bounded window (mode 1) really moves
+    prompt = torch.randint(0, V, (B, T0), generator=g)
+    tmask = torch.rand(B, T0, generator=g) < 0.3
+    prompt[tmask] = torch.randint(s["time"], s["tempo"], (int(tmask.sum()),), generator=g)
+    dist = train_ref.make_distributions("cpu")
+    U = torch.rand(steps, B, 2, generator=g)
+    dev = "cuda"
+    lse = torch.randn(B, V, generator=g).cuda()
+    logits = torch.zeros(B, V, device=dev)
+    counts = torch.zeros(B, V, dtype=torch.int32)
+    gen_py = [row.tolist() for row in prompt]
+    q0, sum0 = torch.zeros(B, dtype=torch.int32), torch.zeros(B, dtype=torch.int32)
+
+    def window(row):
+        if mode == 0:
+            return row[-100:]
+        val, j = 0, 0
+        for j, tok in enumerate(reversed(row)):
+            if s["time"] <= tok < s["tempo"]:
+                val += tok - s["time"]
+            if val >= 64 * 16:
+                break
+        return row[-j:]
+
+    for b in range(B):
+        for t in window(gen_py[b]):
+            counts[b, t] += 1
+        if mode == 1:
+            tv = [t - s["time"] if s["time"] <= t < s["tempo"] else 0 for t in gen_py[b]]
+            q, tot = 0, sum(tv)
+            while q < T0 - 1 and tot - tv[q] >= 64 * 16:
+                tot -= tv[q]
+                q += 1
+            q0[b], sum0[b] = q, tot
+    counts = counts.cuda()
+    generated = torch.zeros(B, T0 + steps + 1, dtype=torch.long, device=dev)
+    generated[:, :T0] = prompt.cuda()
+    gen_len = torch.full((B,), T0, dtype=torch.int32, device=dev)
+    nxt = torch.zeros(B, dtype=torch.long, device=dev)
+    win_q, win_sum = q0.cuda(), sum0.cuda()
+    dist_dev, U_dev = dist.cuda().contiguous(), U.cuda()   # the argument block holds raw pointers: keep the tensors alive
+    args = ops.sample_step_args(mode, logits, lse, dist_dev, counts, generated, gen_len, nxt,
+                                (s["dyn"], s["length"], s["time"], s["tempo"]), T0, uniforms=U_dev, win_q=win_q, win_sum=win_sum)
+    ties = 0
+    for step in range(steps):
+        x = torch.randn(B, V, generator=g) * 3
+        # make repeats likely: boost a few already generated tokens so that penalties matter
+        for b in range(B):
+            x[b, gen_py[b][-3:]] += 6.0
+        logits.copy_(x.cuda())
+        lse_before = lse.cpu().double()
+        ops.sample_step(args, torch.device(dev))
+        torch.cuda.synchronize()
+        got = nxt.cpu().tolist()
+        lse_after = lse.cpu()
+        want_lse = torch.logaddexp(lse_before, x.double())
+        assert_close(lse_after, want_lse.float(), 1e-6, what=f"running logsumexp step {step}")
+        for b in range(B):
+            prev = gen_py[b][-1]
+            bucket = int(torch.bucketize(torch.tensor(prev), torch.tensor([s["dyn"] - 1, s["length"] - 1, s["time"] - 1, s["tempo"] - 1])))
+            f = (-(x[b].double() - lse_after[b].double()) * dist[bucket].double())
+            if mode == 0:
+                c = Counter(gen_py[b][-100:])
+                for tok, cnt in c.items():
+                    if s["tempo"] <= tok:
+                        continue
+                    elif s["time"] <= tok:
+                        pen = 1.1 * cnt if cnt >= 10 else 1
+                    elif s["length"] <= tok:
+                        pen = min(1.015 ** cnt, 1.08)
+                    elif s["dyn"] <= tok:
+                        continue
+                    else:
+                        pen = min(1.04 ** cnt, 1.25)
+                    f[tok] /= pen
+                want = int(f.argmax())
+            else:
+                want = train_ref.choose_sampling(f.clone(), gen_py[b], float(U[step, b, 0]), float(U[step, b, 1]), s)
+            if want != got[b]:
+                top = f.topk(4).values
+                gaps = (top[:-1] - top[1:]) / top[0].abs()
+                assert float(gaps.min()) < 1e-5, (mode, step, b, want, got[b], top)
+                ties += 1
+            gen_py[b].append(got[b])
+        if step % 20 == 0 or step == steps - 1:
+            cnt_dev = counts.cpu()
+            for b in range(B):
+                c = Counter(window(gen_py[b]))
+                dense = torch.zeros(V, dtype=torch.int32)
+                for tok, n in c.items():
+                    dense[tok] = n
+                assert torch.equal(cnt_dev[b], dense), (mode, step, b)
+            assert generated[:, :T0 + step + 1].cpu().tolist() == gen_py
+    assert ties <= 3, ties
