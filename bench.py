@@ -36,6 +36,15 @@ WORKLOAD = ("mamba1_layoutP_d1024_L10_N64_vocab17914 train step (fwd+loss+bwd+al
             "per-GPU batch 2 x 2048 tokens (+6 metadata), bf16 autocast / fp32 residual+scan state")
 
 
+L2_NOTE = ("no explicit flush: one step streams ~1.4 GB of weights/grads/Adam state plus >2 GB of activations, "
+           "far above the 126 MB L2")
+
+
+def workload_config(n_gpus, tokens_per_gpu=4096):
+    """`config` of the JSON line — identical for the b200 arm and the reference (CPU) arm at the same N."""
+    return {"workload": WORKLOAD, "global_batch_tokens": tokens_per_gpu * n_gpus, "parallelism": f"dp{n_gpus}", "l2": L2_NOTE}
+
+
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
@@ -141,17 +150,60 @@ def cpu_reference_sample(steps, warmup, sample_tokens=None):
     return T / mean, mean * 1e3, cores, sample
 
 
+def cpu_kernel_samples():
+    """BASELINE.md section 2 items (i) and (ii) on the host cores, bounded: (i) one MambaBlock forward and
+    forward+backward at the repo's layer shape (d_model 1024, d_state 64) on B=1 x T=512; (ii) the kernel-only
+    selective_scan of config 5 (L=8192, d_state 16, fp32) on a 128-channel slice of the 2048, forward and
+    forward+backward, in the same algorithmic-bytes units as the GPU sweep (cost is linear in B*D)."""
+    import torch
+    from oracle import simple_mamba as om
+    out = {}
+    torch.manual_seed(0)
+    blk = om.MambaBlock(om.ModelArgs(d_model=1024, n_layer=1, vocab_size=17914, d_state=64, pad_vocab_size_multiple=1))
+    x = torch.randn(1, 512, 1024, requires_grad=True)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        blk(x)
+    t_f = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    blk(x).square().sum().backward()
+    t_fb = time.perf_counter() - t0
+    out["mamba_block_repo_shape"] = {"sample": "B=1 x T=512, d_model 1024, d_state 64, fp32", "fwd_ms": t_f * 1e3,
+                                     "fwd_bwd_ms": t_fb * 1e3, "fwd_tokens_per_s": 512 / t_f, "fwd_bwd_tokens_per_s": 512 / t_fb}
+    B, L, D, N = 1, 8192, 128, 16
+    g = torch.Generator().manual_seed(0)
+    u, dl = torch.randn(B, L, D, generator=g), torch.nn.functional.softplus(torch.randn(B, L, D, generator=g) - 4)
+    A = -torch.arange(1, N + 1, dtype=torch.float32).repeat(D, 1)
+    Bm, Cm, Dv = torch.randn(B, L, N, generator=g), torch.randn(B, L, N, generator=g), torch.ones(D)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        om.selective_scan(u, dl, A, Bm, Cm, Dv)
+    t_f = time.perf_counter() - t0
+    leaves = [t.requires_grad_(True) for t in (u, dl, Bm, Cm)]
+    t0 = time.perf_counter()
+    om.selective_scan(leaves[0], leaves[1], A, leaves[2], leaves[3], Dv).sum().backward()
+    t_fb = time.perf_counter() - t0
+    by = algorithmic_bytes(B, L, D, N, 4, 4)
+    out["selective_scan_config5"] = {
+        "sample": f"B={B}, L={L}, D={D} of 2048 channels, d_state {N}, fp32, oracle selective_scan (python loop over L)",
+        "fwd_ms": t_f * 1e3, "fwd_bwd_ms": t_fb * 1e3, "fwd_algo_gbs": by["mamba_scan_fwd"] / t_f / 1e9,
+        "fwd_bwd_algo_gbs": (by["mamba_scan_fwd"] + by["mamba_scan_bwd"]) / t_fb / 1e9,
+        "fwd_elements_per_s": B * L * D * N / t_f}
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    steps = max(1, min(args.steps, int(os.environ.get("MAMBA_B200_CPU_MAX_STEPS", "6"))))
-    warmup = max(1, min(args.warmup, 1))
+    # a step of the sample is ~5 s on 16 cores: the driver's usual --steps 20 --warmup 5 runs in full (~2 min)
+    steps = max(1, min(args.steps, int(os.environ.get("MAMBA_B200_CPU_MAX_STEPS", "20"))))
+    warmup = max(1, min(args.warmup, int(os.environ.get("MAMBA_B200_CPU_MAX_WARMUP", "5"))))
     tps, ms, cores, sample = cpu_reference_sample(steps, warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": tps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "parallelism": "cpu"},
+        "dtype": "f32", "data": "synthetic", "config": workload_config(args.gpus),
         "cpu_baseline": {"value": tps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": tps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -178,6 +230,25 @@ def algorithmic_bytes(B, L, D, N, K, s):
 
 
 MUFU_EX2_PEAK = 4.6e12  # ex2/s, measured on this pool's B200 with tools/microbench.cu (16 lanes/clk/SM at 1.965 GHz)
+
+
+# FMA-pipe cost of one (b, t, d, n) element in SMSP-cycles per warp-pair of 64 elements, from tools/microbench3.cu:
+# two-operand packed FMUL2 2.13 clk, packed FFMA2 with three distinct register pairs 4.27 clk (half lane rate).
+# forward: 2 FMUL2 + 2 FFMA2 per state pair; backward (recompute + sweep): 6 FMUL2 + 6 FFMA2.
+FMA_CLK_PER_PAIR = {"mamba_scan_fwd": 2 * 2.13 + 2 * 4.27, "mamba_scan_bwd": 6 * 2.13 + 6 * 4.27}
+SM_CLOCK_HZ, N_SM = 1.965e9, 148
+
+
+def fma_view(name, B, L, D, N, mean_us):
+    """The scans' other binding pipe: packed fp32 multiply-adds with register operands.  Peak elements/s if the FMA
+    pipe of every SM did nothing else (measured instruction rates above)."""
+    clk = FMA_CLK_PER_PAIR.get(name)
+    if clk is None:
+        return None
+    peak = 4 * 64 / clk * N_SM * SM_CLOCK_HZ       # 4 SMSPs x 64 elements per warp-pair
+    rate = B * L * D * N / (mean_us * 1e-6)
+    return {"pipe": "fma_fp32x2_register_operands", "achieved": rate, "peak": peak, "unit": "elements/s", "frac": rate / peak,
+            "peak_source": "measured instruction rates (tools/microbench3.cu, profiles/r02_microbench_fma_operands.txt)"}
 
 
 def mufu_view(name, B, L, D, N, mean_us):
@@ -216,11 +287,10 @@ def kernel_times(trainer, batches, reps=3):
 
 
 def extras(dev, peak):
-    """(a) kernel-only selective-scan sweep at BASELINE configs[4] (L=8192, N=16, D=2048) and at the repo's training
-    shape, fp32, CUDA events, L2 flushed between launches; (b) recurrent greedy decode, 10 sequences (5 composer
-    conditions x 2), 2048-token prompt."""
+    """Kernel-only selective-scan sweep at BASELINE configs[4] (L=8192, N=16, D=2048) and at the repo's training
+    shape, fp32, CUDA events, L2 flushed between launches."""
     import torch
-    from mamba_b200 import generate, ops, synthetic, train
+    from mamba_b200 import ops
     out = {"scan_sweep": [], "peak_gbs": peak}
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     for name, (B, L, D, N) in (("config5_B2_L8192_N16", (2, 8192, 2048, 16)), ("config5_B8_L8192_N16", (8, 8192, 2048, 16)),
@@ -259,26 +329,47 @@ def extras(dev, peak):
                                   "elem_per_s": B * L * D * N / (t_f * 1e-6)})
         del leaves, o, u, z, dl, Bm, Cm, dout
     del flush
+    return out
+
+
+def decode_leg(dev, rank, world, barrier, n_new=2000, n_seq=10, prompt=2048):
+    """Autoregressive generation (BASELINE configs[3]): prefill + `n_new` recurrent steps per sequence, greedy
+    (scripts/generate_midi_many.py) with the on-device sampler; the sequences are sharded over the ranks."""
+    import torch
+    import torch.distributed as dist
+    from mamba_b200 import generate, synthetic, train
+    lo, hi = train.shard_rows(n_seq, rank, world)
     torch.manual_seed(0)
     model = train.new_model("mamba").to(dev).eval()
-    src, _, meta = synthetic.batch(10, 2048, seed=3)
-    with torch.no_grad():
-        dec = generate.RecurrentDecoder(model, 10, use_graph=True)
-        dec.prefill(src.to(dev), meta.to(dev))
-        for _ in range(8):
-            dec.step()
-        torch.cuda.synchronize()
-        n = 200
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(n):
-            dec.step()
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
-    out["decode"] = {"sequences": 10, "prompt": 2048, "timed_tokens_per_seq": n, "dtype": "f32", "ms_per_step": ms / n,
-                     "tokens_per_sec": 10 * n / (ms * 1e-3), "mode": "recurrent step kernels, one CUDA graph per token, greedy"}
-    return out
+    src, _, meta = synthetic.batch(n_seq, prompt, seed=3)
+    ms = 0.0
+    if hi > lo:
+        with torch.no_grad():
+            dec = generate.RecurrentDecoder(model, hi - lo, use_graph=True, max_new_tokens=n_new + 16)
+            dec.prefill(src[lo:hi].to(dev), meta[lo:hi].to(dev))
+            for _ in range(8):
+                dec.step()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n_new - 9):
+                dec.step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            toks = dec.tokens()
+    else:
+        barrier()
+    barrier()
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    n = n_new - 9
+    return {"sequences": n_seq, "sequences_per_rank_max": -(-n_seq // world), "prompt": prompt, "new_tokens_per_seq": n_new,
+            "timed_steps": n, "dtype": "f32", "ms_per_step": ms / n, "tokens_per_sec": n_seq * n / (ms * 1e-3),
+            "sharding": f"{n_seq} sequences over {world} rank(s), no collective",
+            "mode": "recurrent decode: 4 launches per layer + head + on-device sampler, one CUDA graph per token, greedy"}
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -381,10 +472,8 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": args.dtype, "data": "synthetic",
-        "config": {"workload": WORKLOAD, "global_batch_tokens": B * T * world, "parallelism": f"dp{world}",
-                   "cuda_graph": not args.no_graph,
-                   "l2": "no explicit flush: one step streams ~1.4 GB of weights/grads/Adam state plus >2 GB of "
-                         "activations, far above the 126 MB L2"},
+        "config": workload_config(world, B * T),
+        "cuda_graph": not args.no_graph,
         "clocks": clocks,
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps, "clocks": clocks_e2e},
@@ -393,6 +482,22 @@ def main():
         "loss": loss_dev,
     }
 
+    # ---- BASELINE config 4: 2000 new tokens for 10 sequences (5 composer bands x 2), sharded by sequence over the ranks
+    #      (no collective on the data path; the barrier and the MAX over ranks are measurement only) ---------------------
+    if not args.no_extras:
+        try:
+            line["decode"] = decode_leg(dev, rank, world, barrier)
+        except Exception as e:
+            line["decode"] = {"error": str(e)[:200]}
+    if world > 1:
+        # data-parallel correctness in the record: every rank must hold the same parameters after the timed steps
+        flat = torch.cat([p.detach().flatten().float() for p in model.parameters()])
+        hi, lo = flat.clone(), flat.clone()
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        line["cross_rank_param_max_abs_diff"] = float((hi - lo).max())
+        line["param_checksum_rank0"] = float(flat.double().sum())
+        del flat, hi, lo
     if world > 1:
         # Every collective of the run is behind us.  Ranks > 0 leave now; rank 0 goes on with rank-local
         # measurements.  (No destroy_process_group: tearing NCCL down under a live CUDA graph that holds captured
@@ -425,18 +530,26 @@ def main():
         d = per_kernel[dom]
         # DRAM traffic of the dominant kernel per launch, from the committed ncu --set full capture of the same
         # shape (only valid for the bf16 default workload it was taken on)
-        traffic = None
-        try:
-            if args.dtype == "bf16":
-                traffic = json.loads((ROOT / "profiles" / "r01_ncu_traffic.json").read_text())[dom]["traffic_bytes"]
-        except Exception:
-            traffic = None
+        traffic, traffic_src = None, None
+        if args.dtype == "bf16":
+            for tag in ("r02", "r01"):   # newest capture of this kernel at this shape (the kernel's source hash is in the file)
+                try:
+                    rec = json.loads((ROOT / "profiles" / f"{tag}_ncu_traffic.json").read_text())[dom]
+                    traffic, traffic_src = rec["traffic_bytes"], f"profiles/{tag}_ncu_traffic.json ({rec.get('capture', 'ncu --set full')})"
+                    break
+                except Exception:
+                    continue
         line["roofline"] = {"kernel": dom, "bound": "hbm", "achieved": d["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                            "frac": d["frac_of_hbm_peak"], "traffic": traffic, "peak_source": peak_src,
+                            "frac": d["frac_of_hbm_peak"], "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                             "mean_us": d["mean_us"], "algorithmic_bytes": d["algorithmic_bytes"],
                             "binding_pipe": mufu_view(dom, B, T + cc.N_META, p.d_inner, p.d_state, d["mean_us"]),
-                            "note": "d_state=64 makes this kernel MUFU/FMA-bound, not HBM-bound (SURVEY.md F8); "
-                                    "see profiles/ for the ncu pipe utilisation"}
+                            "binding_pipes": [v for v in (mufu_view(dom, B, T + cc.N_META, p.d_inner, p.d_state, d["mean_us"]),
+                                                          fma_view(dom, B, T + cc.N_META, p.d_inner, p.d_state, d["mean_us"])) if v],
+                            "kernel_times": "eager step bracketed by CUDA events per C-ABI call (shares of the step; `value` "
+                                            "times the graph replay)",
+                            "note": "d_state=64 makes this kernel bound by the MUFU and FMA pipes and by issue slots together, "
+                                    "not by HBM (SURVEY.md F8, DESIGN.md section 4); the fractions are of each pipe alone on "
+                                    "all 148 SMs (the grid covers 128); see profiles/ for the ncu pipe utilisation"}
         line["kernels"] = per_kernel
         # ---- the other two figures of BASELINE.json's metric, N=1 only (short runs; tools/bench_scan.py and
         #      tools/bench_decode.py are the full versions) ---------------------------------------------------------
@@ -450,6 +563,10 @@ def main():
             tps, ms, cores, sample = cpu_reference_sample(steps=2, warmup=1)
             line["cpu_baseline"] = {"value": tps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                                     "ms_per_step": ms}
+            try:
+                line["cpu_baseline"]["kernels"] = cpu_kernel_samples()
+            except Exception as e:
+                line["cpu_baseline"]["kernels"] = {"error": str(e)[:200]}
         print(json.dumps(line), flush=True)
     if world > 1:
         sys.stdout.flush()

@@ -130,14 +130,17 @@ def test_full_model_bf16_autocast_step_loss_and_gradients_vs_fp32_oracle():
     """(d) The benchmarked configuration: Layout P, d_model 1024, 10 layers, d_state 64, B=2 x T=2048, bf16 autocast
     (fp32 residual stream and scan state) against the fp32 oracle on the same weights and batch.
 
-    Stated tolerance: loss within 1e-2 relative.  Per parameter, with e = ||g - g_ref|| / ||g_ref|| (relative L2
-    error against the fp32 oracle): e <= max(0.05, 3 * e_torch), where e_torch is the same error of the ORACLE
-    ITSELF run under torch's bf16 autocast on the same weights and batch (ten layers of bf16 GEMMs with 2^-9 input
-    rounding each: the deepest parameters - the embeddings - see the sum of all of them), and never above 0.25;
-    cosine similarity >= 0.97.  The factor 3 covers what the product rounds in addition to torch autocast: the
-    mixer's intermediate activations (conv output, dt, gate, scan output) are STORED in bf16 between kernels,
-    where the oracle under autocast keeps them in fp32 (measured: 1.6x on the metadata embedding).  Parameters whose reference gradient is numerically zero (below 1e-6 of the
-    largest gradient) are held to that same absolute bound."""
+    Stated tolerance: loss within 1e-2 relative.  Gradients are held to a YARDSTICK, not to a constant: the oracle
+    ITSELF run under torch's bf16 autocast on the same weights and batch.  At this depth and at random init that run
+    is 15-25 % (relative L2) away from the fp32 oracle on most parameters (measured, printed below) - ten layers of
+    bf16 GEMMs on a loss of ~5e2 - so a fixed few-percent bound would test nothing.  Per parameter, with
+    e = ||g - g_ref|| / ||g_ref|| and c = cosine(g, g_ref) against the fp32 oracle:
+        e <= max(0.05, 1.7 * e_torch)      and      1 - c <= max(0.03, 2 * (1 - c_torch)),
+    e_torch / c_torch being the same quantities for the oracle under autocast.  The factor 1.7 covers what the
+    product rounds in addition to torch autocast: the mixer's intermediate activations (conv output, dt, gate, scan
+    output) are STORED in bf16 between kernels where the oracle under autocast keeps them in fp32 (measured: 1.6x on
+    the metadata embedding, 1.02-1.05x elsewhere).  Parameters whose reference gradient is numerically zero (below
+    1e-6 of the largest gradient) are held to that same absolute bound."""
     from mamba_b200 import synthetic, train
     from mamba_b200.models.mamba import Mamba, ModelArgs
     torch.manual_seed(0)
@@ -182,11 +185,12 @@ def test_full_model_bf16_autocast_step_loss_and_gradients_vs_fp32_oracle():
         rel = float((gg - gr).norm() / gr.norm())
         rel_torch = float((g_auto[name] - gr).norm() / gr.norm())
         cos = float(F.cosine_similarity(gg.flatten(), gr.flatten(), dim=0))
+        cos_torch = float(F.cosine_similarity(g_auto[name].flatten(), gr.flatten(), dim=0))
         if rel > worst[0]:
             worst = (rel, cos, name, rel_torch)
         if rel > 0.03:
-            print(f"[fullsize] {name}: rel-L2 {rel:.3e} (oracle under torch autocast {rel_torch:.3e}) cos {cos:.5f}")
-        assert rel <= min(0.25, max(0.05, 3 * rel_torch)) and cos >= 0.97, (name, rel, rel_torch, cos)
+            print(f"[fullsize] {name}: rel-L2 {rel:.3e} (oracle under torch autocast {rel_torch:.3e}) cos {cos:.5f} ({cos_torch:.5f})")
+        assert rel <= max(0.05, 1.7 * rel_torch) and 1 - cos <= max(0.03, 2 * (1 - cos_torch)), (name, rel, rel_torch, cos, cos_torch)
     print(f"[fullsize] worst parameter gradient: {worst[2]} rel-L2 {worst[0]:.3e} (oracle under torch autocast: "
           f"{worst[3]:.3e}) cos {worst[1]:.5f}")
 
