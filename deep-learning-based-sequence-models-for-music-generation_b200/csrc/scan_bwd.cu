@@ -24,6 +24,8 @@
 //     dy = dout*silu(z)), post-pass (finish d_delta (softplus'), d_u (+D*dy), dz from the saved pre-gate output,
 //     accumulate dD / d_bias, 128-bit stores, per-CTA dB/dC partial -> workspace).
 //   * a finalize kernel reduces the per-CTA / per-batch partials in a fixed order (deterministic, no atomics).
+#include <cstdlib>
+
 #include "scan_bwd.cuh"
 
 namespace mb {
@@ -485,6 +487,22 @@ __global__ void scan_bwd_finalize_kernel(const ScanBwdParams p, int rows_per_blo
     const int64_t row0 = (int64_t)blockIdx.x * rows_per_block;  // row = b * L + t
     const int64_t nrows = (int64_t)p.B * p.L;
     const int64_t ts = (int64_t)p.L * p.N;
+    if (p.fixed_acc) {
+      // the tiles already added their partials into one fixed-point accumulator per (b, t, n): convert and store
+      const long long* aB = reinterpret_cast<const long long*>(p.ws_dB);
+      const long long* aC = reinterpret_cast<const long long*>(p.ws_dC);
+      const int nel = rows_per_block * p.N;
+      for (int i = tid; i < nel; i += blockDim.x) {
+        const int64_t row = row0 + i / p.N;
+        const int n = i % p.N;
+        if (row >= nrows) break;
+        const int b = (int)(row / p.L);
+        const int64_t t = row - (int64_t)b * p.L;
+        IO<T>::st(static_cast<T*>(p.dB) + (int64_t)b * p.dB_bs + t * p.dB_ls + n, (float)aB[row * p.N + n] * kAccInvScale);
+        IO<T>::st(static_cast<T*>(p.dC) + (int64_t)b * p.dC_bs + t * p.dC_ls + n, (float)aC[row * p.N + n] * kAccInvScale);
+      }
+      return;
+    }
     if ((p.N & 3) == 0) {
       // 4 states per thread: 16-byte loads of the per-tile partials, 8 of them in flight (4 interleaved partial
       // sums per array, combined in a fixed order)
@@ -645,6 +663,18 @@ static int bwd_dispatch(ScanBwdParams& p, int nper, cudaStream_t stream) {
     if (p.N != 64 && p.N != 32)
       return set_error(MAMBA_EINVAL, "scan_bwd: variant 1 (fused, tensor-pipe reductions) needs d_state 32 or 64 (got %d)", p.N);
     p.NW = p.N / 8, p.NPT = p.N;
+    // Fixed-point accumulation of dB / dC across the channel tiles (scan_bwd.cuh), opt-in with
+    // MAMBA_B200_BWD_FIXED_ACC=1: it removes the [B][ntiles][L][N] partial tensors (DRAM traffic per launch 366 MB ->
+    // ~235 MB, finalize 40 us -> 5 us) but the 33.6 M 64-bit atomics per launch cost more than they save — measured
+    // 765 us against 737 us per backward at the training shape (profiles/r02_summary.md) — so the per-tile partials
+    // stay the default.  Needs the 8-byte slots to fit in the partial workspace (two tiles or more).
+    static const bool fixed = [] { const char* e = getenv("MAMBA_B200_BWD_FIXED_ACC"); return e && e[0] == '1'; }();
+    p.fixed_acc = (fixed && p.ntiles >= 2) ? 1 : 0;
+    if (p.fixed_acc) {
+      const size_t bytes = (size_t)p.B * p.L * p.N * 8;
+      cudaMemsetAsync(p.ws_dB, 0, bytes, stream);
+      cudaMemsetAsync(p.ws_dC, 0, bytes, stream);
+    }
     const int rc = launch_scan_bwd_fused<T>(p, stream);
     return rc ? rc : launch_finalize<T>(p, stream);
   }

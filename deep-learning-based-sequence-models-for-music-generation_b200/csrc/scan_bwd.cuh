@@ -24,7 +24,20 @@ struct ScanBwdParams {
   float *ws_dA;          // [B][N][D]
   float *ws_dD, *ws_db;  // [B][D]
   int vec_u, vec_delta, vec_z, vec_dout, vec_ypre, vec_B, vec_C, vec_ck, vec_du, vec_ddelta, vec_dz;
+  // fixed_acc: the channel tiles add their dB / dC partials into ONE [B][L][N] accumulator (the memory of ws_dB /
+  // ws_dC reused as int64) with 64-bit integer atomics on fixed-point values — integer addition is associative, so
+  // the result does not depend on the order in which the tiles arrive (deterministic), and the [B][ntiles][L][N]
+  // partial tensors (134 MB written + 269 MB re-read per layer at the training shape) disappear.
+  int fixed_acc;
 };
+
+// fixed point of the dB / dC accumulators: 2^-36 resolution (1.5e-11), +-1.3e8 range per accumulator
+constexpr float kAccScale = 68719476736.f;        // 2^36
+constexpr float kAccInvScale = 1.f / 68719476736.f;
+__device__ __forceinline__ void red_add_fixed(float* slot_as_i64, float v) {
+  const long long q = __float2ll_rn(v * kAccScale);
+  asm volatile("red.global.add.u64 [%0], %1;" ::"l"(slot_as_i64), "l"(q) : "memory");
+}
 
 template <int NPER>
 __device__ __forceinline__ void lds_vec(float (&dst)[NPER], const float* src) {

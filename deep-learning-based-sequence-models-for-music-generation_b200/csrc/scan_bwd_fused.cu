@@ -571,8 +571,18 @@ __global__ void __launch_bounds__((NW + kBHelperWarps) * 32, 1) scan_bwd_fused_k
           sB.x += xb.x, sB.y += xb.y, sB.z += xb.z, sB.w += xb.w;
           sC.x += xc.x, sC.y += xc.y, sC.z += xc.z, sC.w += xc.w;
         }
-        reinterpret_cast<float4*>(wsB)[i] = sB;
-        reinterpret_cast<float4*>(wsC)[i] = sC;
+        if (p.fixed_acc) {
+          // one accumulator per (b, t, n): 8-byte slots in the same workspace, [B][L][N]
+          long long* aB = reinterpret_cast<long long*>(p.ws_dB) + ((int64_t)b * p.L + t0) * p.N + 4 * (int64_t)i;
+          long long* aC = reinterpret_cast<long long*>(p.ws_dC) + ((int64_t)b * p.L + t0) * p.N + 4 * (int64_t)i;
+          red_add_fixed(reinterpret_cast<float*>(aB + 0), sB.x), red_add_fixed(reinterpret_cast<float*>(aB + 1), sB.y);
+          red_add_fixed(reinterpret_cast<float*>(aB + 2), sB.z), red_add_fixed(reinterpret_cast<float*>(aB + 3), sB.w);
+          red_add_fixed(reinterpret_cast<float*>(aC + 0), sC.x), red_add_fixed(reinterpret_cast<float*>(aC + 1), sC.y);
+          red_add_fixed(reinterpret_cast<float*>(aC + 2), sC.z), red_add_fixed(reinterpret_cast<float*>(aC + 3), sC.w);
+        } else {
+          reinterpret_cast<float4*>(wsB)[i] = sB;
+          reinterpret_cast<float4*>(wsC)[i] = sC;
+        }
       }
     }
   };

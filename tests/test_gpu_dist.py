@@ -56,12 +56,16 @@ def _worker(rank, world, port, q, mode):
             ddp = torch.nn.parallel.DistributedDataParallel(model, device_ids=[rank])
             opt = torch.optim.Adam(ddp.parameters(), lr=1e-3)
             for _ in range(3):
-                losses.append(float(train.train_step(ddp, opt, s, t, m)))
+                losses.append(float(train.train_step(ddp, opt, s, t, m).detach()))
         torch.cuda.synchronize()
-        flat = torch.cat([p.detach().flatten() for p in model.parameters()]).cpu()
+        flat = torch.cat([p.detach().flatten() for p in model.parameters()]).cpu().numpy()   # by value, not by fd
         q.put((rank, flat, losses))
+        q.close()
+        q.join_thread()
     finally:
-        dist.destroy_process_group()
+        # no destroy_process_group: tearing NCCL down under a live CUDA graph that holds captured all-reduces can
+        # hang (bench.py leaves the same way)
+        os._exit(0)
 
 
 def _run(mode):
@@ -72,11 +76,14 @@ def _run(mode):
     procs = [ctx.Process(target=_worker, args=(r, world, port, q, mode)) for r in range(world)]
     for p in procs:
         p.start()
-    res = sorted((q.get(timeout=600) for _ in range(world)), key=lambda r: r[0])
-    for p in procs:
-        p.join(timeout=120)
-        assert p.exitcode == 0
-    return res
+    try:
+        res = sorted((q.get(timeout=240) for _ in range(world)), key=lambda r: r[0])
+    finally:
+        for p in procs:
+            p.join(timeout=30)
+            if p.is_alive():
+                p.kill()
+    return [(r, torch.from_numpy(f), l) for r, f, l in res]
 
 
 def _single_rank_reference():
