@@ -84,7 +84,7 @@ class FusedLinearStepArgs(C.Structure):
 class SampleStepArgs(C.Structure):
     _fields_ = [("struct_size", i32), ("mode", i32), ("batch", i32), ("vocab", i32), ("bucket_bounds", i32 * 4),
                 ("class_bounds", i32 * 4), ("pen_rule", i32 * 5), ("prompt_len", i32), ("time_budget", i32),
-                ("reserved", i32), ("pen_base", C.c_double * 5), ("pen_cap", C.c_double * 5),
+                ("reserved", i32), ("pen_table", fp),
                 ("logits", fp), ("logits_bs", i64), ("lse", fp), ("dist", fp), ("counts", vp),
                 ("generated", vp), ("generated_bs", i64), ("gen_len", vp), ("next_token", vp), ("uniforms", fp),
                 ("win_q", vp), ("win_sum", vp)]

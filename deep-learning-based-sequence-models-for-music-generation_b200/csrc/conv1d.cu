@@ -59,6 +59,24 @@ struct Vec<T, 1> {
   static __device__ __forceinline__ void st(T* p, const float (&v)[1]) { IO<T>::st(p, v[0]); }
 };
 
+// The thread's VEC x K filter taps.  [D][K] row-major: with K == 4 a channel's taps are one 16-byte vector (the scalar
+// form cost 16 load instructions and 512 L1 sectors per warp — more L1 traffic than the activations, ncu r02)
+template <int VEC, int K>
+__device__ __forceinline__ void load_taps(const float* __restrict__ w, int dv, int D, float (&out)[K][VEC]) {
+  if constexpr (K == 4) {
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(w + (int64_t)min(dv + v, D - 1) * 4));
+      out[0][v] = t.x, out[1][v] = t.y, out[2][v] = t.z, out[3][v] = t.w;
+    }
+  } else {
+#pragma unroll
+    for (int v = 0; v < VEC; ++v)
+#pragma unroll
+      for (int k = 0; k < K; ++k) out[k][v] = w[(int64_t)min(dv + v, D - 1) * K + k];
+  }
+}
+
 // One row of a thread's tile: loaded unconditionally from a clamped timestep (so that all of a thread's loads
 // are independent of each other and of any branch) and zeroed afterwards if the timestep is outside [0, L).
 template <typename T, int VEC>
@@ -83,12 +101,9 @@ __global__ void __launch_bounds__(32 * kConvWarps) conv_fwd_kernel(const ConvPar
   T* out = static_cast<T*>(p.out) + (int64_t)b * p.out_bs + dv;
 
   float w[K][VEC], bias[VEC];
+  load_taps<VEC, K>(p.w, dv, p.D, w);
 #pragma unroll
-  for (int v = 0; v < VEC; ++v) {
-    bias[v] = p.bias ? p.bias[dv + v] : 0.f;
-#pragma unroll
-    for (int k = 0; k < K; ++k) w[k][v] = p.w[(int64_t)(dv + v) * K + k];
-  }
+  for (int v = 0; v < VEC; ++v) bias[v] = p.bias ? p.bias[dv + v] : 0.f;
   float xr[kConvTS + K - 1][VEC];  // xr[i] = x[t0 - (K-1) + i]
 #pragma unroll
   for (int i = 0; i < kConvTS + K - 1; ++i) ld_row_clamped<T, VEC>(x, p.x_ls, t0 - (K - 1) + i, p.L, xr[i]);
@@ -130,7 +145,7 @@ __global__ void __launch_bounds__(32 * kConvWarps) conv_fwd_kernel(const ConvPar
 // Backward.  dpre[t] = dout[t] * silu'(pre[t]);  dx[t] = sum_k w[k] * dpre[t + (K-1) - k];
 // dw[k] = sum_{b,t} dpre[t] * x[t-(K-1)+k];  dbias = sum dpre.
 template <typename T, int VEC, int K>
-__global__ void __launch_bounds__(32 * kConvWarps) conv_bwd_kernel(const ConvParams p) {
+__global__ void __launch_bounds__(32 * kConvWarps, 2) conv_bwd_kernel(const ConvParams p) {   // <= 128 registers: two blocks per SM
   __shared__ float red[kConvWarps][K + 1][32 * VEC];
   const int dv = (blockIdx.x * 32 + threadIdx.x) * VEC;
   const int seg = blockIdx.y * kConvWarps + threadIdx.y;
@@ -149,12 +164,9 @@ __global__ void __launch_bounds__(32 * kConvWarps) conv_bwd_kernel(const ConvPar
     const T* dout = static_cast<const T*>(p.dout) + (int64_t)b * p.dout_bs + dv;
     T* dx = static_cast<T*>(p.dx) + (int64_t)b * p.dx_bs + dv;
     float w[K][VEC], bias[VEC];
+    load_taps<VEC, K>(p.w, dv, p.D, w);
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) {
-      bias[v] = p.bias ? p.bias[dv + v] : 0.f;
-#pragma unroll
-      for (int k = 0; k < K; ++k) w[k][v] = p.w[(int64_t)(dv + v) * K + k];
-    }
+    for (int v = 0; v < VEC; ++v) bias[v] = p.bias ? p.bias[dv + v] : 0.f;
     // rows needed: x[t0-(K-1) .. t1+K-2] and dout[t0 .. t1+K-2] (dx[t] needs dpre[t .. t+K-1])
     constexpr int NX = kConvTS + 2 * (K - 1), ND = kConvTS + K - 1;
     float xr[NX][VEC], dp[ND][VEC];
@@ -271,6 +283,8 @@ static int conv_common(const MambaConvArgs* a, bool bwd, void* stream) {
                      a->dim);
   if (a->batch > 65535) return set_error(MAMBA_ESIZE, "conv1d: batch %d above 65535", a->batch);
   if (!a->x || !a->weight) return set_error(MAMBA_EINVAL, "conv1d: null x/weight");
+  if (a->width == 4 && !mb::aligned16(a->weight))
+    return set_error(MAMBA_EALIGN, "conv1d: weight [D, 4] must be 16-byte aligned (one vector load per channel)");
   if (!bwd && !a->out) return set_error(MAMBA_EINVAL, "conv1d_fwd: null out");
   if (bwd && (!a->dout || !a->dx || !a->dweight)) return set_error(MAMBA_EINVAL, "conv1d_bwd: null dout/dx/dweight");
   if (a->dtype != MAMBA_F32 && a->dtype != MAMBA_BF16) return set_error(MAMBA_EDTYPE, "conv1d: dtype %d", a->dtype);

@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(kSampleThreads) sample_step_kernel(const Mamba
       const int cls = (v >= a.class_bounds[0]) + (v >= a.class_bounds[1]) + (v >= a.class_bounds[2]) + (v >= a.class_bounds[3]);
       const int rule = a.pen_rule[cls];
       float pen = 1.f;
-      if (rule == 1) pen = (float)fmin(pow(a.pen_base[cls], (double)c), a.pen_cap[cls]);   // python: min(base ** count, cap)
+      if (rule == 1) pen = a.pen_table[cls * 128 + min(c, 127)];                           // python: min(base ** count, cap)
       else if (rule == 2) pen = c >= 10 ? (float)(1.1 * (double)c) : 1.f;                  // generate_midi_many.py:33-35
       f = f / pen;
     }
@@ -149,8 +149,8 @@ extern "C" int mamba_sample_step(const MambaSampleStepArgs* a, void* stream) {
     return set_error(MAMBA_EINVAL, "sample_step: bad args pointer or struct_size");
   if (a->batch <= 0 || a->vocab <= 0) return set_error(MAMBA_EINVAL, "sample_step: batch/vocab must be positive");
   if (a->mode != 0 && a->mode != 1) return set_error(MAMBA_EINVAL, "sample_step: mode must be 0 (greedy) or 1 (top-k draw)");
-  if (!a->logits || !a->lse || !a->dist || !a->counts || !a->generated || !a->gen_len || !a->next_token)
-    return set_error(MAMBA_EINVAL, "sample_step: null logits/lse/dist/counts/generated/gen_len/next_token");
+  if (!a->logits || !a->lse || !a->dist || !a->counts || !a->generated || !a->gen_len || !a->next_token || !a->pen_table)
+    return set_error(MAMBA_EINVAL, "sample_step: null logits/lse/dist/counts/generated/gen_len/next_token/pen_table");
   if (a->mode == 1 && (!a->uniforms || !a->win_q || !a->win_sum))
     return set_error(MAMBA_EINVAL, "sample_step: mode 1 needs uniforms, win_q and win_sum");
   launch_chain(sample_step_kernel, dim3(a->batch), dim3(kSampleThreads), 0, static_cast<cudaStream_t>(stream), *a);

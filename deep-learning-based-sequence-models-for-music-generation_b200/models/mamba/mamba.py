@@ -1,19 +1,16 @@
 """Drop-in mirror of the reference's Mamba modules, running on the sm_100a kernels of libmamba_b200.so.
 
-Same class names, constructor arguments and call signatures as the reference; parameter names/shapes (hence
-state_dict layout) are identical for Layout P and for the OUTER keys of Layout S only — see the warning below:
+Same class names, constructor arguments, call signatures and parameter names/shapes (hence state_dict layout) as the
+reference, for both model layouts:
   * `ModelArgs`, `Mamba(params)`, `ResidualBlock`, `MambaBlock`, `RMSNorm` — the pure-PyTorch Mamba-1 of
     models/mamba/__pycache__/simple_mamba.cpython-311.pyc (source deleted upstream; SURVEY.md Appendix A;
     `@Lnnn` = original source line).  "Layout P": keys embedding / metadata_embedding /
     layers.{i}.mixer.* / layers.{i}.norm.weight / norm_f.weight / lm_head.weight (tied).
-  * `Mamba(d_model=1024, n_layers=10)` — the shipped wrapper's signature (models/mamba/mamba.py:8-35):
-    keys token_embedding / metadata_embedding / output_layer / layers.{i}.* / norm; no residuals, final
-    LayerNorm, untied head with bias.  Its layers here are `MambaBlock`s (the Mamba-1 maths that
-    BASELINE.json's north_star names); the external mamba_ssm.Mamba2 it stacks upstream is out of scope.
-    NOT CHECKPOINT-COMPATIBLE with the reference's shipped model: upstream `layers.{i}` are Mamba2 modules
-    (in_proj [4256,1024], conv1d over 2176 channels, A_log/D/dt_bias [32], gated norm — SURVEY Appendix B), here
-    they are Mamba-1 blocks (x_proj, dt_proj, A_log [2048,64]); the constructor warns once about it and
-    `load_state_dict` of a reference checkpoint fails on the layer keys by design.
+  * `Mamba(d_model=1024, n_layers=10)` — the shipped wrapper (models/mamba/mamba.py:8-35), "Layout S": keys
+    token_embedding / metadata_embedding / output_layer / layers.{i}.* / norm; no residuals, final LayerNorm,
+    untied head with bias.  Its layers are `mamba2.Mamba2` (mamba_ssm.Mamba2's parameters and arithmetic on this
+    repo's kernels), so a checkpoint of the reference's shipped model loads; parity for that layer is UNPINNED
+    (mamba_ssm is outside the reference tree — oracle/mamba2_ref.py restates the published recurrence).
 Both forms take `forward(tokens[B,T] long, meta[B,6] long)` and return logits `[B, T, V]` (first 6
 positions dropped, mamba.py:35 / simple_mamba @L96).
 
@@ -408,17 +405,15 @@ class Mamba(nn.Module):
         super().__init__()
         if isinstance(d_model, int):
             self.layout = "S"
-            warnings.warn(
-                "mamba_b200.Mamba(d_model, n_layers): the shipped wrapper's signature and OUTER state_dict keys, but its "
-                "layers are Mamba-1 blocks (the hot path BASELINE.json names), not mamba_ssm.Mamba2: checkpoints of the "
-                "reference's shipped model do not load into it and its outputs differ.  Use Mamba(get_mamba_dict()) "
-                "(Layout P) for the checkpoint-compatible pure-PyTorch Mamba-1.", stacklevel=2)
             params = _params_from_configs(d_model, n_layers)
             self.params = params
             self.token_embedding = nn.Embedding(cc.vocab_size, d_model)            # mamba.py:12
             self.metadata_embedding = nn.Embedding(cc.metadata_vocab_size, d_model)  # :13
             self.output_layer = nn.Linear(d_model, cc.vocab_size)                  # :14
-            self.layers = nn.ModuleList([MambaBlock(params, layer_idx=i) for i in range(n_layers)])  # :16-24
+            from .mamba2 import Mamba2
+            mv = cm.config.model_values
+            self.layers = nn.ModuleList([Mamba2(d_model=d_model, d_state=mv.d_state, d_conv=mv.d_conv, expand=mv.expand,
+                                                layer_idx=i) for i in range(n_layers)])            # :16-24
             self.norm = nn.LayerNorm(d_model)                                      # :25
         else:
             self.layout = "P"

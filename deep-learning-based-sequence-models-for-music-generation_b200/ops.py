@@ -675,8 +675,11 @@ def sample_step_args(mode, logits, lse, dist, counts, generated, gen_len, next_t
     else:           # scripts/generate.py:60-71
         rule, base, cap = (1, 1, 0, 0, 0), (1.01, 1.02, 1.0, 1.0, 1.0), (1.2, 1.2, 1.0, 1.0, 1.0)
     a.pen_rule = (ct.c_int32 * 5)(*rule)
-    a.pen_base = (ct.c_double * 5)(*base)
-    a.pen_cap = (ct.c_double * 5)(*cap)
+    # min(base ** count, cap) for count 0..127, in python doubles exactly as the reference loops evaluate it (every
+    # cap is reached below count 20, so the table's last column is the value for any larger count)
+    table = torch.tensor([[min(b ** c, k) for c in range(128)] for b, k in zip(base, cap)], dtype=torch.float64)
+    a._pen_table = table.to(torch.float32).to(logits.device).contiguous()    # kept alive by the argument block
+    a.pen_table = _p(a._pen_table)
     a.prompt_len, a.time_budget = int(prompt_len), 64 * 16
     a.logits, a.logits_bs = _p(logits), logits.stride(0)
     a.lse, a.dist, a.counts = _p(lse), _p(dist), _p(counts)

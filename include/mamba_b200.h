@@ -286,11 +286,12 @@ typedef struct MambaSampleStepArgs {
   int32_t batch, vocab;
   int32_t bucket_bounds[4]; /* {dyn-1, length-1, time-1, tempo-1}: torch.bucketize boundaries of train.py:114-131 */
   int32_t class_bounds[4];  /* {dyn, length, time, tempo}: first token id of each class after pitch             */
-  int32_t pen_rule[5];      /* per token class: 0 none, 1 min(base**count, cap), 2 (1.1*count if count >= 10)    */
+  int32_t pen_rule[5];      /* per token class: 0 none, 1 pen_table[class][min(count, 127)], 2 (1.1*count if count >= 10) */
   int32_t prompt_len;
   int32_t time_budget;      /* mode 1: 64*16 (scripts/generate.py:43) */
   int32_t reserved;
-  double pen_base[5], pen_cap[5];
+  const float* pen_table;   /* [5, 128] fp32: min(base ** count, cap) per token class, tabulated by the caller in double
+                               precision exactly as the python loops evaluate it (every cap is reached below count 20) */
   const float* logits;  int64_t logits_bs;   /* [B, V] fp32: the model's output for the last position */
   float* lse;               /* [B, V] running logsumexp over the positions seen so far (updated) */
   const float* dist;        /* [5, V] weights of train.make_distributions (train.py:79-111)     */

@@ -72,11 +72,11 @@ def test_model_logits_loss_and_grads_fp32(layout):
         ref = om.Mamba(_args(om.ModelArgs))
         model = Mamba(_args(ModelArgs))
     else:
-        ref = om.ShippedWrapper(_args(om.ModelArgs), d_model=64, n_layers=2)
-        model = Mamba(d_model=64, n_layers=2)
-        # the shipped-signature constructor reads d_state etc. from configs: rebuild the oracle to match
-        ref = om.ShippedWrapper(om.ModelArgs(d_model=64, n_layer=2, vocab_size=17914, d_state=model.params.d_state,
-                                             expand=2, d_conv=4, pad_vocab_size_multiple=1), d_model=64, n_layers=2)
+        # the shipped wrapper: Mamba-2 layers (oracle/mamba2_ref.py restates the published recurrence; parity for this
+        # layer is unpinned — mamba_ssm is outside the reference tree)
+        from oracle.mamba2_ref import ShippedMambaRef
+        model = Mamba(d_model=128, n_layers=2)
+        ref = ShippedMambaRef(d_model=128, n_layers=2, d_state=model.params.d_state)
     _randomise(ref, 2)
     model.load_state_dict(ref.state_dict(), strict=True)
     model.cuda()
@@ -99,6 +99,54 @@ def test_model_logits_loss_and_grads_fp32(layout):
             assert float(gp[name].grad.abs().max()) < 1e-5 * gmax, name
             continue
         assert_close(gp[name].grad, p.grad, RTOL32, 2e-5, what=f"{layout} d{name}")
+
+
+@pytest.mark.parametrize("cfg", [dict(d_model=128, d_state=64), dict(d_model=64, d_state=16, headdim=32)])
+def test_mamba2_layer_forward_backward_fp32(cfg):
+    """The shipped model's layer (mamba_ssm.Mamba2 as configured at models/mamba/mamba.py:17-23) on the hot path's
+    kernels against oracle/mamba2_ref.py (a restatement of the published recurrence: parity UNPINNED, mamba_ssm is
+    not in the reference tree): output and every parameter / input gradient, fp32 rtol 1e-4."""
+    from mamba_b200.models.mamba.mamba2 import Mamba2
+    from oracle.mamba2_ref import Mamba2Ref
+    torch.manual_seed(0)
+    ref = Mamba2Ref(**cfg)
+    _randomise(ref, 3)
+    with torch.no_grad():
+        ref.dt_bias.copy_(torch.randn_like(ref.dt_bias) - 3)      # softplus(dt + bias) ~ 0.05
+        ref.A_log.copy_(torch.log(torch.rand_like(ref.A_log) * 15 + 1))
+    lay = Mamba2(**cfg)
+    lay.load_state_dict(ref.state_dict(), strict=True)
+    lay.cuda()
+    x = torch.randn(2, 70, cfg["d_model"], generator=torch.Generator().manual_seed(4))
+    xr = x.clone().requires_grad_(True)
+    yr = ref(xr)
+    g = torch.randn_like(yr)
+    yr.backward(g)
+    xg = x.cuda().requires_grad_(True)
+    yg = lay(xg)
+    yg.backward(g.cuda())
+    assert_close(yg, yr, RTOL32, what="mamba2 out")
+    assert_close(xg.grad, xr.grad, RTOL32, 2e-5, what="mamba2 dx")
+    gp = dict(lay.named_parameters())
+    for name, p in ref.named_parameters():
+        assert_close(gp[name].grad, p.grad, RTOL32, 2e-5, what=f"mamba2 d{name}")
+
+
+def test_layout_s_prefill_and_step_match_full_forward():
+    """Recurrent decode of the shipped (Mamba-2) layout: prefill + step logits equal the full forward's."""
+    from mamba_b200 import synthetic
+    from mamba_b200.models.mamba import Mamba
+    torch.manual_seed(0)
+    model = Mamba(d_model=128, n_layers=2).cuda().eval()
+    src, _, meta = synthetic.batch(3, 40, seed=6)
+    with torch.no_grad():
+        full = model(src.cuda(), meta.cuda())
+        cache = model.allocate_inference_cache(3)
+        pre = model.prefill(src[:, :25].cuda(), meta.cuda(), cache)
+        assert_close(pre, full[:, :25], RTOL32, 2e-5, what="layout S prefill logits")
+        for t in range(25, 40):
+            lg = model.step(src[:, t].cuda(), cache)
+            assert_close(lg, full[:, t], RTOL32, 2e-5, what=f"layout S step logits t={t}")
 
 
 def test_model_bf16_autocast_tolerance():

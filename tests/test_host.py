@@ -65,14 +65,31 @@ def test_state_dict_layout_matches_oracle_layout_p():
 
 
 def test_state_dict_layout_shipped_wrapper():
-    m = Mamba(d_model=32, n_layers=2)
+    """Layout S = models/mamba/mamba.py:8-35 with mamba_ssm.Mamba2 layers: outer keys, Mamba-2 parameter names and
+    shapes, identical to the oracle restatement, and loadable both ways."""
+    from oracle.mamba2_ref import ShippedMambaRef
+    m = Mamba(d_model=64, n_layers=2)
     keys = list(m.state_dict().keys())
     assert keys[:4] == ["token_embedding.weight", "metadata_embedding.weight", "output_layer.weight",
                         "output_layer.bias"]
-    assert "layers.1.out_proj.weight" in keys and keys[-2:] == ["norm.weight", "norm.bias"]
-    ref = om.ShippedWrapper(_small_args(om.ModelArgs), d_model=32, n_layers=2)
-    assert list(ref.state_dict().keys()) == keys
-    assert m.token_embedding.weight.shape == (17914, 32)
+    assert keys[-2:] == ["norm.weight", "norm.bias"]
+    layer = {k.split(".", 2)[2]: tuple(v.shape) for k, v in m.state_dict().items() if k.startswith("layers.1.")}
+    d_inner, N, H = 128, 64, 2
+    assert layer == {"dt_bias": (H,), "A_log": (H,), "D": (H,), "in_proj.weight": (2 * d_inner + 2 * N + H, 64),
+                     "conv1d.weight": (d_inner + 2 * N, 1, 4), "conv1d.bias": (d_inner + 2 * N,),
+                     "norm.weight": (d_inner,), "out_proj.weight": (64, d_inner)}
+    ref = ShippedMambaRef(d_model=64, n_layers=2, d_state=64)
+    assert sorted(ref.state_dict().keys()) == sorted(keys)
+    m.load_state_dict(ref.state_dict(), strict=True)
+    ref.load_state_dict(m.state_dict(), strict=True)
+    assert m.token_embedding.weight.shape == (17914, 64)
+
+
+def test_shipped_model_parameter_count_is_the_number_the_reference_prints():
+    """scripts/Test Accuracy.ipynb:52 prints 101,972,666 trainable parameters for Mamba(d_model=1024, n_layers=10):
+    the one quantitative anchor the reference gives for the shipped (Mamba-2) layout."""
+    m = Mamba(d_model=1024, n_layers=10)
+    assert sum(p.numel() for p in m.parameters() if p.requires_grad) == 101_972_666
 
 
 def test_block_init_matches_reference_init():
