@@ -15,6 +15,7 @@ EXPORTS = [
     "mamba_scan_fwd", "mamba_scan_ckpt_elems", "mamba_scan_bwd", "mamba_scan_bwd_workspace_bytes",
     "mamba_conv1d_silu_fwd", "mamba_conv1d_silu_bwd", "mamba_conv1d_bwd_workspace_bytes",
     "mamba_conv_step", "mamba_ssm_step", "mamba_linear_step", "mamba_fused_linear_step", "mamba_sample_step",
+    "mamba_decode_token", "mamba_decode_token_scratch_bytes",
     "mamba_rmsnorm_fwd", "mamba_rmsnorm_bwd", "mamba_rmsnorm_bwd_workspace_bytes",
     "mamba_filtered_ce_fwd", "mamba_filtered_ce_bwd", "mamba_filtered_ce_workspace_bytes",
 ]
@@ -90,6 +91,20 @@ class SampleStepArgs(C.Structure):
                 ("win_q", vp), ("win_sum", vp)]
 
 
+class DecodeLayer(C.Structure):
+    _fields_ = [("norm_weight", fp), ("in_proj_weight", vp), ("in_proj_bias", vp), ("conv_weight", fp), ("conv_bias", fp),
+                ("conv_state", fp), ("x_proj_weight", vp), ("dt_weight", fp), ("dt_bias", fp), ("A", fp), ("D", fp),
+                ("ssm_state", fp), ("out_proj_weight", vp), ("out_proj_bias", vp)]
+
+
+class DecodeTokenArgs(C.Structure):
+    _fields_ = [("struct_size", i32), ("w_dtype", i32), ("batch", i32), ("n_layers", i32), ("vocab", i32),
+                ("d_model", i32), ("d_inner", i32), ("d_state", i32), ("dt_rank", i32), ("d_conv", i32),
+                ("eps", C.c_float), ("reserved", i32), ("token", vp), ("embedding", vp), ("layers", vp),
+                ("norm_f_weight", fp), ("head_weight", vp), ("head_bias", vp), ("logits", fp), ("logits_bs", i64),
+                ("scratch", fp), ("scratch_bytes", sz), ("barrier", vp)]
+
+
 class LossArgs(C.Structure):
     _fields_ = [("struct_size", i32), ("dtype", i32), ("batch", i32), ("seqlen", i32), ("vocab", i32),
                 ("boundaries", i32 * 4), ("reserved", i32),
@@ -124,10 +139,12 @@ def lib() -> C.CDLL:
                        ("mamba_rmsnorm_fwd", NormArgs), ("mamba_rmsnorm_bwd", NormArgs),
                        ("mamba_filtered_ce_fwd", LossArgs), ("mamba_filtered_ce_bwd", LossArgs),
                        ("mamba_linear_step", LinearStepArgs), ("mamba_fused_linear_step", FusedLinearStepArgs),
-                       ("mamba_sample_step", SampleStepArgs)):
+                       ("mamba_sample_step", SampleStepArgs), ("mamba_decode_token", DecodeTokenArgs)):
         f = getattr(L, name)
         f.restype = C.c_int
         f.argtypes = [C.POINTER(argt), C.c_void_p]
+    L.mamba_decode_token_scratch_bytes.restype = sz
+    L.mamba_decode_token_scratch_bytes.argtypes = [C.c_int] * 4
     L.mamba_scan_ckpt_elems.restype = sz
     L.mamba_scan_ckpt_elems.argtypes = [C.c_int] * 5
     L.mamba_scan_bwd_workspace_bytes.restype = sz

@@ -70,15 +70,16 @@ def generate_literal(model, context_len, token_ids, meta_ids, num_tokens=1000):
 class RecurrentDecoder:
     """Prefill + CUDA-graphed single-token step for a fixed batch of independent sequences.
 
-    One step = embedding lookup, 4 launches per layer (`Mamba.step`'s fused path), the head with the final norm
-    folded in, and ONE launch of `mamba_sample_step` that applies filtered_logit, the repetition penalties, picks
-    the token, appends it to `generated` and advances the look-back window (csrc/sample.cu).
+    One step = ONE launch of `mamba_decode_token` (csrc/decode.cu: the whole model as one persistent cooperative
+    kernel; Layout P, fp32 states) — or, for models it does not cover, the embedding lookup + 4 launches per layer of
+    `Mamba.step`'s fused path + the head — and ONE launch of `mamba_sample_step`, which applies filtered_logit and the
+    repetition penalties, picks the token, appends it to `generated` and advances the look-back window.
     mode "many":   greedy, scripts/generate_midi_many.py:13-56.
     mode "sample": top-k draw of scripts/generate.py:14-95; `uniforms` [max_new, B, 2] supplies the randomness
                    (default: torch.rand from `generator`, i.e. a Philox stream with a fixed seed)."""
 
     def __init__(self, model, batch_size, use_graph=True, dtype=None, mode="many", max_new_tokens=4096, uniforms=None,
-                 generator=None):
+                 generator=None, persistent=None, weight_dtype=None):
         if mode not in ("many", "sample"):
             raise ValueError("mode must be 'many' or 'sample'")
         self.model = model.eval()
@@ -102,6 +103,16 @@ class RecurrentDecoder:
         self.use_graph = use_graph
         self.graph = None
         self.sargs = None
+        # one-launch-per-token path (csrc/decode.cu): default whenever the model qualifies; `weight_dtype=torch.bfloat16`
+        # streams decode-only bf16 copies of the weight matrices (activations, states and accumulation stay fp32)
+        self.plan = None
+        want = ops.DecodeTokenPlan.eligible(model, self.cache, batch_size) if persistent is None else bool(persistent)
+        if want:
+            if not ops.DecodeTokenPlan.eligible(model, self.cache, batch_size):
+                raise ValueError("RecurrentDecoder(persistent=True): model / cache not supported by mamba_decode_token")
+            self.plan = ops.DecodeTokenPlan(model, self.cache, self.nxt, self.logits, weight_dtype)
+        elif weight_dtype is not None:
+            raise ValueError("weight_dtype needs the persistent decode kernel")
 
     @torch.no_grad()
     def prefill(self, token_ids, meta_ids):
@@ -148,7 +159,10 @@ class RecurrentDecoder:
         return self.nxt.clone()
 
     def _step_body(self):
-        self.model.step(self.nxt, self.cache, logits_out=self.logits)
+        if self.plan is not None:
+            self.plan.run()                                   # the whole model, one cooperative launch
+        else:
+            self.model.step(self.nxt, self.cache, logits_out=self.logits)
         ops.sample_step(self.sargs, self.dev)
 
     @torch.no_grad()
@@ -195,11 +209,12 @@ class RecurrentDecoder:
 
 @torch.no_grad()
 def generate_recurrent(model, token_ids, meta_ids, num_tokens=1000, use_graph=True, dtype=None, mode="many",
-                       uniforms=None, generator=None):
+                       uniforms=None, generator=None, persistent=None, weight_dtype=None):
     """`num_tokens` new tokens for each row of token_ids; returns [B, T + num_tokens].  mode "many": greedy
     (scripts/generate_midi_many.py); mode "sample": the top-k draw of scripts/generate.py with the given uniforms."""
     dec = RecurrentDecoder(model, token_ids.shape[0], use_graph=use_graph, dtype=dtype, mode=mode,
-                           max_new_tokens=num_tokens, uniforms=uniforms, generator=generator)
+                           max_new_tokens=num_tokens, uniforms=uniforms, generator=generator, persistent=persistent,
+                           weight_dtype=weight_dtype)
     dec.prefill(token_ids, meta_ids)
     for _ in range(1, num_tokens):
         dec.step()

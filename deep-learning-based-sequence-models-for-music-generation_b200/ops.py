@@ -19,7 +19,7 @@ import torch
 
 from . import _lib
 from ._lib import (FLAG_A_IS_LOG, FLAG_DELTA_SOFTPLUS, FLAG_HAS_D, FLAG_HAS_DELTA_BIAS, FLAG_HAS_Z, MAMBA_BF16, MAMBA_F32, ConvArgs,
-                   FusedLinearStepArgs, LinearStepArgs, SampleStepArgs, LossArgs, NormArgs, ScanBwdArgs, ScanFwdArgs, StepArgs, check, lib)
+                   DecodeLayer, DecodeTokenArgs, FusedLinearStepArgs, LinearStepArgs, SampleStepArgs, LossArgs, NormArgs, ScanBwdArgs, ScanFwdArgs, StepArgs, check, lib)
 
 _DTYPES = {torch.float32: MAMBA_F32, torch.bfloat16: MAMBA_BF16}
 
@@ -691,6 +691,80 @@ def sample_step_args(mode, logits, lse, dist, counts, generated, gen_len, next_t
 
 def sample_step(args, device):
     _call("mamba_sample_step", args, device)
+
+
+class DecodeTokenPlan:
+    """Argument block of mamba_decode_token (the whole-model, one-launch decode step) for a Layout-P model and its
+    inference cache.  Holds every tensor the raw pointers refer to (weights — optionally bf16 copies made here —,
+    step constants, the device array of layer descriptors, scratch, barrier words)."""
+
+    SHAPES = ((1024, 2048), (128, 256))
+
+    @staticmethod
+    def eligible(model, cache, batch):
+        p = getattr(model, "params", None)
+        if getattr(model, "layout", None) != "P" or p is None or batch > 16:
+            return False
+        w = model.layers[0].mixer.in_proj.weight
+        return ((p.d_model, p.d_inner) in DecodeTokenPlan.SHAPES and p.d_state % 4 == 0 and p.dt_rank % 4 == 0 and w.is_cuda
+                and w.dtype == torch.float32 and all(cs.dtype == torch.float32 for cs, _ in cache)
+                and model.lm_head.bias is None)
+
+    def __init__(self, model, cache, token, logits, weight_dtype=None):
+        p = model.params
+        dev = token.device
+        wdt = weight_dtype or torch.float32
+        self.keep = []
+
+        def W(t):   # a weight in the streaming dtype (bf16: a decode-only copy)
+            t = t.detach()
+            t = t if t.dtype == wdt else t.to(wdt)
+            t = t.contiguous()
+            self.keep.append(t)
+            return t
+
+        def F32(t):
+            if t is None:
+                return None
+            t = t.detach().float().contiguous()
+            self.keep.append(t)
+            return t
+
+        layers = (DecodeLayer * len(model.layers))()
+        for i, (layer, (cs, hs)) in enumerate(zip(model.layers, cache)):
+            m, d = layer.mixer, layers[i]
+            d.norm_weight = _p(F32(layer.norm.weight))
+            d.in_proj_weight, d.in_proj_bias = _p(W(m.in_proj.weight)), _p(None if m.in_proj.bias is None else W(m.in_proj.bias))
+            d.conv_weight = _p(F32(m.conv1d.weight).view(p.d_inner, p.d_conv))
+            d.conv_bias = _p(F32(m.conv1d.bias))
+            d.conv_state, d.ssm_state = _p(cs), _p(hs)
+            d.x_proj_weight = _p(W(m.x_proj.weight))
+            d.dt_weight, d.dt_bias = _p(F32(m.dt_proj.weight)), _p(F32(m.dt_proj.bias))
+            d.A, d.D = _p(F32(-torch.exp(m.A_log.detach().float()))), _p(F32(m.D))
+            d.out_proj_weight = _p(W(m.out_proj.weight))
+            d.out_proj_bias = _p(None if m.out_proj.bias is None else W(m.out_proj.bias))
+        raw = bytes(layers)
+        self.layers_dev = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
+        n = lib().mamba_decode_token_scratch_bytes(p.d_model, p.d_inner, p.d_state, p.dt_rank)
+        self.scratch = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self.barrier = torch.zeros(2, dtype=torch.int32, device=dev)
+        self.token, self.logits = token, logits
+        a = DecodeTokenArgs()
+        a.struct_size = ct.sizeof(DecodeTokenArgs)
+        a.w_dtype = _DTYPES[wdt]
+        a.batch, a.n_layers, a.vocab = token.shape[0], len(model.layers), model.embedding.weight.shape[0]
+        a.d_model, a.d_inner, a.d_state, a.dt_rank, a.d_conv = p.d_model, p.d_inner, p.d_state, p.dt_rank, p.d_conv
+        a.eps = float(model.norm_f.eps)
+        emb = W(model.embedding.weight)
+        a.token, a.embedding, a.layers = _p(token), _p(emb), _p(self.layers_dev)
+        a.norm_f_weight, a.head_weight, a.head_bias = _p(F32(model.norm_f.weight)), _p(emb), None   # tied head
+        a.logits, a.logits_bs = _p(logits), logits.stride(0)
+        a.scratch, a.scratch_bytes, a.barrier = _p(self.scratch), n, _p(self.barrier)
+        self.args = a
+        self.device = dev
+
+    def run(self):
+        _call("mamba_decode_token", self.args, self.device)
 
 
 def launch_count() -> int:

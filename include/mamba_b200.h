@@ -307,6 +307,55 @@ typedef struct MambaSampleStepArgs {
 int mamba_sample_step(const MambaSampleStepArgs* args, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * One new token through the whole model in ONE persistent kernel (csrc/decode.cu; Layout P, fp32 activations and
+ * states, fp32 or bf16 weights, batch <= 16).  Per layer: RMSNorm(hidden + resid) -> in_proj -> conv step + SiLU ->
+ * x_proj -> dt_proj + softplus + SSM step + D skip + gate -> out_proj  (simple_mamba.pyc @L179, @L228-245 for one
+ * position), then the final norm and the LM head (@L94): the 42 launches of the step-by-step path (mamba_fused_linear_step,
+ * mamba_linear_step, mamba_ssm_step) become one cooperative grid (one CTA per SM) with a grid barrier between phases.
+ * `layers` is a DEVICE array of n_layers descriptors; `token` [B] int64 is read on the device (it is the sampler's
+ * output of the previous step); `logits` [B, vocab] fp32 feeds mamba_sample_step.  conv_state / ssm_state are updated
+ * in place.  `scratch` (mamba_decode_token_scratch_bytes) and `barrier` (2 x uint32) are caller-owned.
+ * Supported shapes: (d_model, d_inner) = (1024, 2048) or (128, 256); d_state % 4 == 0, dt_rank % 4 == 0.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct MambaDecodeLayer {
+  const float* norm_weight;       /* [d_model] RMSNorm of the residual block                 */
+  const void* in_proj_weight;     /* [2*d_inner, d_model]  (w_dtype)                         */
+  const void* in_proj_bias;       /* [2*d_inner] or NULL                                      */
+  const float* conv_weight;       /* [d_inner, d_conv]                                        */
+  const float* conv_bias;         /* [d_inner] or NULL                                        */
+  float* conv_state;              /* [B, d_inner, d_conv] fp32, updated                       */
+  const void* x_proj_weight;      /* [dt_rank + 2*d_state, d_inner]  (w_dtype)                */
+  const float* dt_weight;         /* [d_inner, dt_rank] fp32                                  */
+  const float* dt_bias;           /* [d_inner] or NULL                                        */
+  const float* A;                 /* [d_inner, d_state] (= -exp(A_log))                       */
+  const float* D;                 /* [d_inner] or NULL                                        */
+  float* ssm_state;               /* [B, d_inner, d_state] fp32, updated                      */
+  const void* out_proj_weight;    /* [d_model, d_inner]  (w_dtype)                            */
+  const void* out_proj_bias;      /* [d_model] or NULL                                        */
+} MambaDecodeLayer;
+
+typedef struct MambaDecodeTokenArgs {
+  int32_t struct_size;
+  int32_t w_dtype;
+  int32_t batch, n_layers, vocab;
+  int32_t d_model, d_inner, d_state, dt_rank, d_conv;
+  float eps;
+  int32_t reserved;
+  const int64_t* token;           /* [B] the token each sequence consumes                    */
+  const void* embedding;          /* [vocab, d_model]  (w_dtype)                              */
+  const MambaDecodeLayer* layers; /* DEVICE array [n_layers]                                  */
+  const float* norm_f_weight;     /* [d_model]                                                */
+  const void* head_weight;        /* [vocab, d_model]  (w_dtype; the tied embedding)          */
+  const void* head_bias;          /* [vocab] or NULL                                          */
+  float* logits;  int64_t logits_bs;  /* [B, vocab] fp32                                      */
+  float* scratch; size_t scratch_bytes;
+  unsigned int* barrier;          /* 2 x uint32, any contents                                 */
+} MambaDecodeTokenArgs;
+
+size_t mamba_decode_token_scratch_bytes(int d_model, int d_inner, int d_state, int dt_rank);
+int mamba_decode_token(const MambaDecodeTokenArgs* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * RMSNorm with fused residual add.  Replaces RMSNorm.forward (simple_mamba.pyc @L346) and the
  * `+ x` of ResidualBlock.forward (@L179):
  *     r = x + residual   (either operand may be NULL, not both; the sum is rounded to resid_dtype

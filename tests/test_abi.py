@@ -39,7 +39,8 @@ def test_ctypes_struct_layout_matches_c(tmp_path):
     structs = {"MambaScanFwdArgs": _lib.ScanFwdArgs, "MambaScanBwdArgs": _lib.ScanBwdArgs,
                "MambaConvArgs": _lib.ConvArgs, "MambaStepArgs": _lib.StepArgs, "MambaNormArgs": _lib.NormArgs,
                "MambaLossArgs": _lib.LossArgs, "MambaLinearStepArgs": _lib.LinearStepArgs,
-               "MambaFusedLinearStepArgs": _lib.FusedLinearStepArgs, "MambaSampleStepArgs": _lib.SampleStepArgs}
+               "MambaFusedLinearStepArgs": _lib.FusedLinearStepArgs, "MambaSampleStepArgs": _lib.SampleStepArgs,
+               "MambaDecodeLayer": _lib.DecodeLayer, "MambaDecodeTokenArgs": _lib.DecodeTokenArgs}
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void){"]
     for cname, ct in structs.items():
         lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')

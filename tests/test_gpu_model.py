@@ -276,6 +276,43 @@ def test_fused_decode_step_equals_unfused_step():
             assert_close(hs1, hs2, rtol, floor, what="ssm state")
 
 
+def test_persistent_decode_kernel_equals_step_by_step_path():
+    """mamba_decode_token (the whole model as ONE cooperative launch per token, csrc/decode.cu) against the
+    kernel-per-op decode path on the same weights: logits of every step within fp32 tolerance, identical greedy
+    tokens, identical final states; then the bf16-weight variant against the fp32 one at bf16 tolerance."""
+    from mamba_b200 import generate, synthetic
+    from mamba_b200.configs import common as cc
+    from mamba_b200.models.mamba import Mamba, ModelArgs
+    torch.manual_seed(0)
+    model = Mamba(ModelArgs(d_model=128, n_layer=3, vocab_size=cc.vocab_size, d_state=16, expand=2, d_conv=4,
+                            pad_vocab_size_multiple=1, metadata_vocab_size=cc.metadata_vocab_size))
+    _randomise(model, 7)
+    model.cuda().eval()
+    src, _, meta = synthetic.batch(5, 60, seed=13)
+    src, meta = src.cuda(), meta.cuda()
+    decs = {}
+    for name, kw in (("steps", dict(persistent=False)), ("one", dict(persistent=True)),
+                     ("one_graph", dict(persistent=True, use_graph=True)), ("one_bf16", dict(persistent=True, weight_dtype=torch.bfloat16))):
+        kw.setdefault("use_graph", False)
+        d = generate.RecurrentDecoder(model, 5, max_new_tokens=64, **kw)
+        d.prefill(src, meta)
+        decs[name] = d
+    assert decs["one"].plan is not None and decs["steps"].plan is None
+    for t in range(40):
+        for d in decs.values():
+            d.step()
+        ref = decs["steps"]
+        assert_close(decs["one"].logits, ref.logits, 1e-4, 2e-5, what=f"persistent decode logits, step {t}")
+        assert torch.equal(decs["one_graph"].logits, decs["one"].logits)
+        assert torch.equal(decs["one"].nxt, ref.nxt), t
+        if t < 3:   # before the sequences can part ways
+            assert_close(decs["one_bf16"].logits, ref.logits, 2e-2, 2e-2, what=f"bf16-weight decode logits, step {t}")
+    for (cs1, hs1), (cs2, hs2) in zip(decs["one"].cache, decs["steps"].cache):
+        assert_close(cs1, cs2, 1e-4, 2e-5, what="conv state")
+        assert_close(hs1, hs2, 1e-4, 2e-5, what="ssm state")
+    assert torch.equal(decs["one"].tokens(), decs["steps"].tokens())
+
+
 def test_trainer_graph_step_equals_eager_step():
     """The CUDA-graphed step (Trainer) and the python-launched reference-shaped step produce the same losses."""
     from mamba_b200 import synthetic, train
