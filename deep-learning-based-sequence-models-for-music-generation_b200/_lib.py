@@ -15,7 +15,7 @@ EXPORTS = [
     "mamba_scan_fwd", "mamba_scan_ckpt_elems", "mamba_scan_bwd", "mamba_scan_bwd_workspace_bytes",
     "mamba_conv1d_silu_fwd", "mamba_conv1d_silu_bwd", "mamba_conv1d_bwd_workspace_bytes",
     "mamba_conv_step", "mamba_ssm_step", "mamba_linear_step", "mamba_fused_linear_step", "mamba_sample_step",
-    "mamba_decode_token", "mamba_decode_token_scratch_bytes",
+    "mamba_decode_token", "mamba_decode_token_scratch_bytes", "mamba_decode_token_barrier_bytes",
     "mamba_rmsnorm_fwd", "mamba_rmsnorm_bwd", "mamba_rmsnorm_bwd_workspace_bytes",
     "mamba_filtered_ce_fwd", "mamba_filtered_ce_bwd", "mamba_filtered_ce_workspace_bytes",
 ]
@@ -100,7 +100,7 @@ class DecodeLayer(C.Structure):
 class DecodeTokenArgs(C.Structure):
     _fields_ = [("struct_size", i32), ("w_dtype", i32), ("batch", i32), ("n_layers", i32), ("vocab", i32),
                 ("d_model", i32), ("d_inner", i32), ("d_state", i32), ("dt_rank", i32), ("d_conv", i32),
-                ("eps", C.c_float), ("reserved", i32), ("token", vp), ("embedding", vp), ("layers", vp),
+                ("eps", C.c_float), ("flags", i32), ("token", vp), ("embedding", vp), ("layers", vp),
                 ("norm_f_weight", fp), ("head_weight", vp), ("head_bias", vp), ("logits", fp), ("logits_bs", i64),
                 ("scratch", fp), ("scratch_bytes", sz), ("barrier", vp)]
 
@@ -145,6 +145,8 @@ def lib() -> C.CDLL:
         f.argtypes = [C.POINTER(argt), C.c_void_p]
     L.mamba_decode_token_scratch_bytes.restype = sz
     L.mamba_decode_token_scratch_bytes.argtypes = [C.c_int] * 4
+    L.mamba_decode_token_barrier_bytes.restype = sz
+    L.mamba_decode_token_barrier_bytes.argtypes = [C.c_int]
     L.mamba_scan_ckpt_elems.restype = sz
     L.mamba_scan_ckpt_elems.argtypes = [C.c_int] * 5
     L.mamba_scan_bwd_workspace_bytes.restype = sz

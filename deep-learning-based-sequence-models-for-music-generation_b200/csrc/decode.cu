@@ -6,46 +6,50 @@
 // final norm and the LM head (@L94).  Launched as separate kernels that is 42 launches of 5-25 us whose time is
 // launch latency, prologues and tails, not the 450 MB of weights and state they stream (profiles/r02_decode_*).
 // Here ONE cooperative grid (one CTA per SM, all co-resident) walks the phases and meets at a grid barrier between
-// them (4 per layer); while a CTA waits at a barrier its warps have already asked L2 for the first weight rows of
-// the next phase.  Activations between phases live in a small global scratch (read with ld.global.cg: they were
-// written by other SMs in the same launch); the residual stream is fp32; weights are fp32 or bf16; batch <= 16.
-//
-// Work split of a linear phase y[b, n] = sum_k W[n, k] x[b, k]: the activation rows sit in shared memory as fp32;
-// a warp owns RW consecutive weight rows per task, lanes stride the K axis with 16-byte loads (every weight byte is
-// read once, all of a task's loads are issued before the first multiply-add), one butterfly per (row, sequence).
-#include <cooperative_groups.h>
-
+// them (4 per layer).  What bounds a phase is latency (DRAM round trip of the weights, L2 round trip of the
+// activations other SMs wrote, the barrier itself), so the kernel is organised around taking those off the critical
+// path:
+//   * the barrier is split into arrive (one release-RED per CTA) and wait (acquire-poll of the same counter); between
+//     the two every warp issues the loads of the NEXT phase that do not depend on this one — its weight rows, the
+//     SSM / conv states, A, dt_proj rows — into registers, so their DRAM latency overlaps the barrier;
+//   * phases with many rows per CTA (in_proj, head) give a warp two weight rows and the whole K axis (lanes stride K
+//     with 16-byte loads; activations in shared memory); K is cut in two register tiles so that the next task's
+//     loads are in flight while this task's second half is multiplied;
+//   * phases with few rows per CTA (x_proj: 192 rows, out_proj: 1024 rows over 148 CTAs) split K over the CTA's 16
+//     warps instead: a warp reads ITS 128-wide slice of the activations straight from L2 into registers (no staging
+//     of the full 80 KB row block, no __syncthreads before the math), lanes = 2 batch halves x 16 K-lanes, four
+//     shuffle steps per output, a fixed-order sum over the warps through 8 KB of shared memory;
+//   * the SSM phase maps a half-warp to (channel, batch parity): A and the dt_proj row are loaded once per channel, the
+//     <= 8 state rows of the half-warp are in registers before the barrier opens.
+// Activations between phases live in a small global scratch (read with ld.global.cg: they were written by other SMs in
+// the same launch); the residual stream is fp32; weights are fp32 or bf16; batch <= 16 (template BMAX = batch rounded
+// up to even; padded rows are zeros and their outputs are dropped).
 #include "common.cuh"
 
 namespace mb {
 
 namespace {
 
-constexpr int kDecThreads = 512;
+constexpr int kDecThreads = 256;   // 8 warps x up to 255 registers: the phases keep whole weight tiles and state rows in registers
 constexpr int kDecWarps = kDecThreads / 32;
 constexpr int kMaxB = 16;
+constexpr int kStampWords = 4;  // barrier words before the time stamps (MAMBA_DECODE_FLAG_STAMPS)
 
-// L2 loads (no L1 allocation): the scratch was written by other SMs earlier in this launch.  Plain intrinsics, so that
-// the compiler can batch them; the grid barrier's fences and "memory" clobbers keep every load inside its phase.
+// L2 loads (no L1 allocation): the scratch was written by other SMs earlier in this launch.
 __device__ __forceinline__ float ldcg(const float* p) { return __ldcg(p); }
 __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 
-// ---- grid barrier: monotone generation counter, one arrival per CTA ------------------------------------------------
-__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int nblocks, unsigned int& gen) {
-  __syncthreads();
+// ---- grid barrier: monotone arrival counter (the host zeroes it before every launch) -----------------------------------
+__device__ __forceinline__ void grid_arrive(unsigned int* bar) {
+  __syncthreads();   // every write of this CTA happens-before thread 0's release
+  if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(bar), "r"(1u) : "memory");
+}
+__device__ __forceinline__ void grid_wait(unsigned int* bar, unsigned int target) {
   if (threadIdx.x == 0) {
-    ++gen;
-    __threadfence();
-    const unsigned int arrived = atomicAdd(bar, 1u) + 1u;
-    if (arrived == gen * nblocks) {
-      asm volatile("st.global.release.gpu.u32 [%0], %1;" ::"l"(bar + 1), "r"(gen) : "memory");
-    } else {
-      unsigned int g;
-      do {
-        asm volatile("ld.global.acquire.gpu.u32 %0, [%1];" : "=r"(g) : "l"(bar + 1) : "memory");
-      } while (g < gen);
-    }
-    __threadfence();
+    unsigned int v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+    } while (v < target);
   }
   __syncthreads();
 }
@@ -64,322 +68,517 @@ __device__ __forceinline__ void ldw4<__nv_bfloat16>(const __nv_bfloat16* p, floa
   w[2] = __uint_as_float(v.y << 16), w[3] = __uint_as_float(v.y & 0xffff0000u);
 }
 
-// pull the first weight rows this warp will own in the NEXT phase into L2 (issued before the grid barrier)
-template <typename TW>
-__device__ __forceinline__ void prefetch_rows(const TW* W, int N, int K, int RW, int gw, int nwarps_total, int lane) {
-  const size_t row_bytes = (size_t)K * sizeof(TW);
-  for (int task = gw; task * RW < N; task += nwarps_total) {
-    for (int r = 0; r < RW; ++r) {
-      const int n = task * RW + r;
-      if (n < N) {
-        const char* p = reinterpret_cast<const char*>(W) + (size_t)n * row_bytes;
-        for (size_t off = (size_t)lane * 128; off < row_bytes; off += 32 * 128) prefetch_l2(p + off);
-      }
-    }
-    break;  // first task only: the rest streams behind it
-  }
+__device__ __forceinline__ float dot4(const float (&w)[4], const float4 x, float acc) {
+  return fmaf(w[3], x.w, fmaf(w[2], x.z, fmaf(w[1], x.y, fmaf(w[0], x.x, acc))));
 }
 
-// One linear phase.  xs: [B][K] fp32 in shared memory.  epi(n, b, value) is called by lane b of the owning warp.
-// The weight rows of a warp's FIRST task are loaded by load_task() before the activations are staged (they do not
-// depend on the previous phase), so the DRAM round trip of the weights overlaps the L2 round trip of the staging.
-template <typename TW, int RW, int KI>
+// ---- "rows" mapping: a warp owns RW weight rows and the whole K axis ---------------------------------------------------------
+// K = NQ chunks x KH x 128 floats; a tile holds rows x KH 16-byte pieces per lane of ONE chunk.  Two tiles form a ring:
+// while chunk q is multiplied, chunk q+1 is already in registers or in flight, and chunk q+2 (of this task or of the
+// warp's next one) is requested as soon as q's tile is free.
+template <int RW, int KH>
 struct WTile {
-  float w[RW][KI][4];
+  float w[RW][KH][4];
 };
-template <typename TW, int RW, int KI>
-__device__ __forceinline__ void load_task(WTile<TW, RW, KI>& t, const TW* __restrict__ W, int N, int K, int task, int lane) {
+template <typename TW, int RW, int KH>
+__device__ __forceinline__ void load_chunk(WTile<RW, KH>& t, const TW* __restrict__ W, int N, int K, int task, int q, int lane) {
   const int n0 = task * RW;
 #pragma unroll
   for (int r = 0; r < RW; ++r) {
-    const TW* wr = W + (size_t)min(n0 + r, N - 1) * K;
+    const TW* wr = W + (size_t)min(n0 + r, N - 1) * K + q * (KH * 128);
 #pragma unroll
-    for (int i = 0; i < KI; ++i) ldw4<TW>(wr + 4 * (lane + 32 * i), t.w[r][i]);
+    for (int i = 0; i < KH; ++i) ldw4<TW>(wr + 4 * (lane + 32 * i), t.w[r][i]);
   }
 }
-template <typename TW, int RW, int KI, typename Epi>
-__device__ __forceinline__ void linear_phase(WTile<TW, RW, KI>& t, const TW* __restrict__ W, const TW* __restrict__ bias, int N,
-                                             int K, int B, const float* xs, int gw, int nwarps_total, int lane, Epi epi) {
-  // KI = K / 128: 16-byte steps per lane (compile time so that all weight loads of a task are in flight together)
-  for (int task = gw; task * RW < N; task += nwarps_total) {
-    const int n0 = task * RW;
-    if (task != gw) load_task<TW, RW, KI>(t, W, N, K, task, lane);
-    float acc[RW][kMaxB];
+template <int RW, int KH, int BMAX>
+__device__ __forceinline__ void mul_chunk(const WTile<RW, KH>& t, const float* xs, int K, int q, int lane, float2 (&acc)[RW][BMAX]) {
+  // packed fp32x2 (FFMA2): .x accumulates the even k of the lane's 16-byte pieces, .y the odd ones
+#pragma unroll
+  for (int i = 0; i < KH; ++i) {
+#pragma unroll
+    for (int b = 0; b < BMAX; ++b) {
+      const float4 xv = *reinterpret_cast<const float4*>(xs + b * K + q * (KH * 128) + 4 * (lane + 32 * i));
+#pragma unroll
+      for (int r = 0; r < RW; ++r) {
+        acc[r][b] = __ffma2_rn(make_float2(t.w[r][i][0], t.w[r][i][1]), make_float2(xv.x, xv.y), acc[r][b]);
+        acc[r][b] = __ffma2_rn(make_float2(t.w[r][i][2], t.w[r][i][3]), make_float2(xv.z, xv.w), acc[r][b]);
+      }
+    }
+  }
+}
+// One "rows" phase.  The first NB chunks of the warp's first task are loaded by the caller (before the grid barrier
+// opens); pre(task) issues a task's other independent loads, epi(r, n, b, value) is called by lane b of the owning warp.
+template <typename TW, int RW, int KH, int NQ, int NB, int BMAX, typename Pre, typename Epi, typename Mark>
+__device__ __forceinline__ void rows_phase(WTile<RW, KH> (&t)[NB], const TW* __restrict__ W, const TW* __restrict__ bias, int N, int K,
+                                           int B, const float* xs, int gw, int nwt, int lane, Pre pre, Epi epi, Mark mark) {
+  static_assert(NQ % NB == 0, "the ring position of a chunk must not depend on the task");
+  for (int task = gw; task * RW < N; task += nwt) {
+    if (task != gw) pre(task);
+    const int nxt = task + nwt;
+    const bool more = nxt * RW < N;
+    float2 acc[RW][BMAX];
 #pragma unroll
     for (int r = 0; r < RW; ++r)
 #pragma unroll
-      for (int b = 0; b < kMaxB; ++b) acc[r][b] = 0.f;
+      for (int b = 0; b < BMAX; ++b) acc[r][b] = make_float2(0.f, 0.f);
+#pragma unroll 1
+    for (int q0 = 0; q0 < NQ; q0 += NB) {   // (rolled: the body is long and the instruction cache is small)
 #pragma unroll
-    for (int i = 0; i < KI; ++i) {
-#pragma unroll
-      for (int b = 0; b < kMaxB; ++b) {
-        if (b < B) {
-          const float4 xv = *reinterpret_cast<const float4*>(xs + b * K + 4 * (lane + 32 * i));
-#pragma unroll
-          for (int r = 0; r < RW; ++r)
-            acc[r][b] = fmaf(t.w[r][i][3], xv.w, fmaf(t.w[r][i][2], xv.z, fmaf(t.w[r][i][1], xv.y, fmaf(t.w[r][i][0], xv.x, acc[r][b]))));
-        }
+      for (int j = 0; j < NB; ++j) {
+        const int q = q0 + j;
+        mul_chunk<RW, KH, BMAX>(t[j], xs, K, q, lane, acc);
+        if (q + NB < NQ)
+          load_chunk<TW, RW, KH>(t[j], W, N, K, task, q + NB, lane);
+        else if (more)
+          load_chunk<TW, RW, KH>(t[j], W, N, K, nxt, q + NB - NQ, lane);
       }
     }
+    mark();
 #pragma unroll
     for (int r = 0; r < RW; ++r) {
       float mine = 0.f;
 #pragma unroll
-      for (int b = 0; b < kMaxB; ++b) {
-        if (b < B) {
-          float v = acc[r][b];
+      for (int b = 0; b < BMAX; ++b) {
+        float v = acc[r][b].x + acc[r][b].y;
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-          if (lane == b) mine = v;
-        }
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == b) mine = v;
       }
-      const int n = n0 + r;
-      if (n < N && lane < B) epi(n, lane, mine + (bias ? IO<TW>::ld(bias + n) : 0.f));
+      const int n = task * RW + r;
+      if (n < N && lane < B) epi(r, n, lane, mine + (bias ? IO<TW>::ld(bias + n) : 0.f));
     }
+  }
+}
+
+// ---- "K-split" mapping: the CTA owns rows blockIdx + j*gridDim (j < RG); warp w owns K-slice w ----------------------------------
+// lane = bq*16 + kq: bq = batch parity (b = bq, bq+2, ...), kq = K-lane.  A warp's slice is K/warps floats, walked in NP
+// pieces of KQ K-lanes x KP 16-byte loads; per piece the RG weight rows and the BH activation rows of the lane are
+// loaded together (one L2 round trip: the weights were prefetched into L2 before the barrier opened), multiplied
+// into acc[RG][BH]; four shuffle steps per output reduce over the K-lanes and the warp's partial sums go to
+// red[warp][j][b].
+template <typename TW, int KQ>
+__device__ __forceinline__ void prefetch_rows_l2(const TW* __restrict__ W, int N, int K, int nrows, int warp, int lane) {
+  // the warp's slice of rows j < nrows: K/warps elements each, one prefetch per 128 bytes
+  const int bytes = (K / kDecWarps) * (int)sizeof(TW);
+  const int pieces = (bytes + 127) >> 7;
+  for (int i = lane; i < nrows * pieces; i += 32) {
+    const int j = i / pieces, piece = i - j * pieces;
+    const int n = blockIdx.x + j * gridDim.x;
+    if (n < N) prefetch_l2(reinterpret_cast<const char*>(W + (size_t)n * K + warp * (K / kDecWarps)) + piece * 128);
+  }
+}
+template <typename TW, int RG, int KQ, int KP, int NP, int BH, int BMAX, int RMAX>
+__device__ __forceinline__ void ksplit_rows(const TW* __restrict__ W, int N, int K, const float* src, int B, float* red, int warp, int kq,
+                                            int bq) {
+  float acc[RG][BH];
+#pragma unroll
+  for (int r = 0; r < RG; ++r)
+#pragma unroll
+    for (int i = 0; i < BH; ++i) acc[r][i] = 0.f;
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    float w[RG][KP][4];
+    float4 x[BH][KP];
+    const int k0 = warp * (K / kDecWarps) + 4 * (p * KP * KQ + kq);   // + 4 * KQ * j
+#pragma unroll
+    for (int r = 0; r < RG; ++r) {
+      const int n = blockIdx.x + r * gridDim.x;
+#pragma unroll
+      for (int j = 0; j < KP; ++j) {
+        if (n < N && kq < KQ)
+          ldw4<TW>(W + (size_t)n * K + k0 + 4 * KQ * j, w[r][j]);
+        else
+          w[r][j][0] = w[r][j][1] = w[r][j][2] = w[r][j][3] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < BH; ++i) {
+      const int b = bq + 2 * i;
+#pragma unroll
+      for (int j = 0; j < KP; ++j)
+        x[i][j] = (b < B && kq < KQ) ? ldcg4(src + (size_t)b * K + k0 + 4 * KQ * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int r = 0; r < RG; ++r)
+#pragma unroll
+      for (int i = 0; i < BH; ++i)
+#pragma unroll
+        for (int j = 0; j < KP; ++j) acc[r][i] = dot4(w[r][j], x[i][j], acc[r][i]);
+  }
+#pragma unroll
+  for (int r = 0; r < RG; ++r)
+#pragma unroll
+    for (int i = 0; i < BH; ++i) {
+      float v = acc[r][i];
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (kq == 0) red[(warp * RMAX + r) * BMAX + bq + 2 * i] = v;
+    }
+}
+// fixed-order sum over the warps; thread (j, b) owns output row blockIdx + j*gridDim of sequence b
+template <typename TW, int BMAX, int RMAX, typename Epi>
+__device__ __forceinline__ void finish_rows(const float* red, const TW* __restrict__ bias, int N, int B, int nrows, Epi epi) {
+  __syncthreads();
+  const int j = threadIdx.x / BMAX, b = threadIdx.x - j * BMAX;
+  const int n = blockIdx.x + j * gridDim.x;
+  if (j < nrows && n < N && b < B) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < kDecWarps; ++w) s += red[(w * RMAX + j) * BMAX + b];
+    epi(n, b, s + (bias ? IO<TW>::ld(bias + n) : 0.f));
   }
 }
 
 // stage s = hidden + resid (or the embedding rows for the first layer), write s as the new residual (CTA 0), and leave
-// rmsnorm(s) * w in shared memory:  `normed, resid = norm(hidden, resid)`  (simple_mamba.pyc @L179 / @L346)
-template <typename TW, int KI>
-__device__ __forceinline__ void stage_norm(float* xs, const float* hidden, const float* resid_in, float* resid_out,
-                                           const TW* emb, const int64_t* tok, const float* norm_w, float eps, int B, int K) {
-  // one warp per sequence; the lane's KI 16-byte pieces of the row are all loaded before the first use (one L2 round
-  // trip per row instead of one per piece)
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int b = warp; b < B; b += kDecWarps) {
-    float* row = xs + b * K;
-    float4 v[KI], g[KI];
-    if (emb != nullptr) {
-      const TW* er = emb + (size_t)tok[b] * K;
+// rmsnorm(s) * w in shared memory:  `normed, resid = norm(hidden, resid)`  (simple_mamba.pyc @L179 / @L346).
+// Thread t owns the 16-byte column pieces t, t + 256, ... of EVERY sequence: all of the CTA's loads are in flight
+// together (one L2 round trip), the per-sequence sums of squares meet in shared memory (fixed order).
+template <typename TW, int K, int BMAX>
+__device__ __forceinline__ void stage_norm(float* xs, float* ssq, const float* hidden, const float* resid_in, float* resid_out,
+                                           const TW* emb, const int64_t* tok, const float* norm_w, float eps, int B) {
+  constexpr int C4 = K / 4;                                              // 16-byte pieces per row
+  constexpr int NC = (C4 + kDecThreads - 1) / kDecThreads;              // ... per thread and row (1)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-      for (int i = 0; i < KI; ++i) {
-        float e[4];
-        ldw4<TW>(er + 4 * (lane + 32 * i), e);
-        v[i] = make_float4(e[0], e[1], e[2], e[3]);
+  for (int c = 0; c < NC; ++c) {
+    const int col = threadIdx.x + c * kDecThreads;
+    const bool on = col < C4;
+    float4 v[BMAX];
+    if (emb != nullptr) {
+#pragma unroll
+      for (int b = 0; b < BMAX; ++b) {
+        float e[4] = {0.f, 0.f, 0.f, 0.f};
+        if (on && b < B) ldw4<TW>(emb + (size_t)tok[b] * K + 4 * col, e);
+        v[b] = make_float4(e[0], e[1], e[2], e[3]);
       }
     } else {
-      float4 h[KI], r[KI];
+      float4 r[BMAX];
 #pragma unroll
-      for (int i = 0; i < KI; ++i) h[i] = ldcg4(hidden + (size_t)b * K + 4 * (lane + 32 * i)), r[i] = ldcg4(resid_in + (size_t)b * K + 4 * (lane + 32 * i));
+      for (int b = 0; b < BMAX; ++b) {
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        v[b] = (on && b < B) ? ldcg4(hidden + (size_t)b * K + 4 * col) : z4;
+        r[b] = (on && b < B) ? ldcg4(resid_in + (size_t)b * K + 4 * col) : z4;
+      }
 #pragma unroll
-      for (int i = 0; i < KI; ++i) v[i] = make_float4(h[i].x + r[i].x, h[i].y + r[i].y, h[i].z + r[i].z, h[i].w + r[i].w);
+      for (int b = 0; b < BMAX; ++b) v[b] = make_float4(v[b].x + r[b].x, v[b].y + r[b].y, v[b].z + r[b].z, v[b].w + r[b].w);
     }
+    float ss[BMAX];
 #pragma unroll
-    for (int i = 0; i < KI; ++i) g[i] = __ldg(reinterpret_cast<const float4*>(norm_w) + lane + 32 * i);
-    float ss = 0.f;
-#pragma unroll
-    for (int i = 0; i < KI; ++i) {
-      if (blockIdx.x == 0 && resid_out) *reinterpret_cast<float4*>(resid_out + (size_t)b * K + 4 * (lane + 32 * i)) = v[i];
-      ss = fmaf(v[i].x, v[i].x, fmaf(v[i].y, v[i].y, fmaf(v[i].z, v[i].z, fmaf(v[i].w, v[i].w, ss))));
+    for (int b = 0; b < BMAX; ++b) {
+      if (on && b < B) {
+        if (blockIdx.x == 0 && resid_out) *reinterpret_cast<float4*>(resid_out + (size_t)b * K + 4 * col) = v[b];
+        *reinterpret_cast<float4*>(xs + b * K + 4 * col) = v[b];
+      }
+      ss[b] = fmaf(v[b].x, v[b].x, fmaf(v[b].y, v[b].y, fmaf(v[b].z, v[b].z, v[b].w * v[b].w)));
     }
+    // reduce-scatter over the warp: after the 5 steps lane b (< BMAX <= 16) holds the warp's sum for sequence b
+    float mine = 0.f;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    const float rstd = rsqrtf(ss / (float)K + eps);
+    for (int b = 0; b < BMAX; ++b) {
+      float t = ss[b];
 #pragma unroll
-    for (int i = 0; i < KI; ++i)
-      *reinterpret_cast<float4*>(row + 4 * (lane + 32 * i)) =
-          make_float4(v[i].x * rstd * g[i].x, v[i].y * rstd * g[i].y, v[i].z * rstd * g[i].z, v[i].w * rstd * g[i].w);
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      if (lane == b) mine = t;
+    }
+    if (lane < BMAX) ssq[(c * kDecWarps + warp) * BMAX + lane] = mine;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const int col = threadIdx.x + c * kDecThreads;
+    if (col < C4) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(norm_w) + col);
+#pragma unroll
+      for (int b = 0; b < BMAX; ++b) {
+        if (b < B) {
+          float tot = 0.f;
+#pragma unroll
+          for (int w = 0; w < NC * kDecWarps; ++w) tot += ssq[w * BMAX + b];
+          const float rstd = rsqrtf(tot / (float)K + eps);
+          float4 v = *reinterpret_cast<float4*>(xs + b * K + 4 * col);
+          v = make_float4(v.x * rstd * g.x, v.y * rstd * g.y, v.z * rstd * g.z, v.w * rstd * g.w);
+          *reinterpret_cast<float4*>(xs + b * K + 4 * col) = v;
+        }
+      }
+    }
   }
 }
 
-__device__ __forceinline__ void stage_rows(float* xs, const float* src, int B, int K) {
-  // up to 8 independent 16-byte loads per thread in flight per round (16 x 2048 floats = 16 per thread at most)
-  const int total = B * K;
-  for (int base = threadIdx.x * 4; base < total; base += kDecThreads * 4 * 8) {
-    float4 v[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int i = base + u * kDecThreads * 4;
-      v[u] = i < total ? ldcg4(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int i = base + u * kDecThreads * 4;
-      if (i < total) *reinterpret_cast<float4*>(xs + i) = v[u];
-    }
-  }
-}
+// registers of the SSM phase that do not depend on x_proj: loaded before the barrier opens
+template <int BH>
+struct SsmPre {
+  float4 A4, w4, h[BH];
+  float dtb, Dd;
+};
 
-template <typename TW>
+constexpr int kRW = 4;   // weight rows per task of the "rows" phases
+
+template <typename TW, int BMAX, bool BIG>
 __global__ void __launch_bounds__(kDecThreads, 1) decode_token_kernel(const MambaDecodeTokenArgs a) {
-  extern __shared__ __align__(16) float xs[];  // [B][max(d_model, d_inner)]
+  constexpr int K1 = BIG ? 1024 : 128;          // d_model
+  constexpr int K2 = BIG ? 2048 : 256;          // d_inner
+  constexpr int NQ1 = BIG ? 4 : 1;              // "rows" phases: chunks along K, tiles in the ring
+  constexpr int NB1 = BIG ? 2 : 1;
+  constexpr int KH1 = K1 / 128 / NQ1;           // 16-byte pieces per lane, row and chunk
+  constexpr int SL4 = K2 / kDecWarps / 4;       // K-split phases: 16-byte pieces per warp slice (64 : 8)
+  constexpr int KQ = SL4 < 16 ? SL4 : 16;       // active K-lanes
+  constexpr int KV = SL4 / KQ;                  // 16-byte pieces per K-lane ...
+  constexpr int KP = KV < 2 ? KV : 2;           // ... loaded KP at a time
+  constexpr int NP = KV / KP;
+  constexpr int RMAX4 = BIG ? 7 : 1;            // out_proj rows per CTA (x_proj: 2; both checked against gridDim by the host)
+  constexpr int BH = BMAX / 2;
+  constexpr int NI = 2;                         // SSM items (channel, batch parity) a half-warp preloads
+  constexpr int kMaxXD = 3 * 64;                // dt_rank + 2 * d_state
+  extern __shared__ __align__(16) float smem[];
+  float* xs = smem;                             // [BMAX][K1] normalised activations of the "rows" phases
+  float* red = xs + BMAX * K1;                  // [warps][8 rows][BMAX] partial sums of the K-split phases
+  float* xd_s = red + kDecWarps * 8 * BMAX;     // [B][XD] x_proj output of every sequence (SSM phase)
+  MambaDecodeLayer* Ls = reinterpret_cast<MambaDecodeLayer*>(xd_s + BMAX * kMaxXD);   // the layer descriptors
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int kq = lane & 15, bq = lane >> 4;
   const int nblk = gridDim.x;
-  const int gw = warp * nblk + blockIdx.x;     // warp w of every CTA before warp w+1 of any: tasks spread over the SMs
+  const int gw = warp * nblk + blockIdx.x;      // warp w of every CTA before warp w+1 of any: tasks spread over the SMs
   const int nwt = nblk * kDecWarps;
-  const int B = a.batch, dm = a.d_model, di = a.d_inner, N = a.d_state, R = a.dt_rank, KC = a.d_conv;
+  const int B = a.batch, N = a.d_state, R = a.dt_rank;
   const int XD = R + 2 * N;
-#ifdef MB_DEC_PROFILE
-  unsigned long long* stamps = reinterpret_cast<unsigned long long*>(a.barrier + 4);
   int nstamp = 0;
-  auto stamp = [&]() {
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
+  auto stamp = [&](int id) {   // (id << 56 | ns) per event, CTA 0 thread 0
+    if ((a.flags & MAMBA_DECODE_FLAG_STAMPS) && blockIdx.x == 0 && threadIdx.x == 0) {
       unsigned long long t;
       asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-      stamps[nstamp] = t;
+      reinterpret_cast<unsigned long long*>(a.barrier + kStampWords)[nstamp++] = ((unsigned long long)id << 56) | (t & 0xffffffffffffffull);
     }
-    ++nstamp;
   };
-#else
-  auto stamp = []() {};
-#endif
-  stamp();
-  unsigned int gen = 0;                         // the host zeroes both barrier words before every launch
-  unsigned int* bar = a.barrier;
-  // scratch carve-up (fp32)
-  float* resid[2] = {a.scratch, a.scratch + (size_t)kMaxB * dm};
-  float* hidden = resid[1] + (size_t)kMaxB * dm;
-  float* zbuf = hidden + (size_t)kMaxB * dm;
-  float* xc = zbuf + (size_t)kMaxB * di;
-  float* xdbl = xc + (size_t)kMaxB * di;
-  float* ybuf = xdbl + (size_t)kMaxB * XD;
-  const TW* emb = static_cast<const TW*>(a.embedding);
+  stamp(0);
+  unsigned int target = 0;
+  // scratch carve-up (fp32): resid[2] | hidden | z | xc | x_dbl | y
+  auto resid = [&](int i) { return a.scratch + (size_t)(i & 1) * kMaxB * K1; };
+  float* const hidden = a.scratch + (size_t)2 * kMaxB * K1;
+  float* const zbuf = a.scratch + (size_t)3 * kMaxB * K1;
+  float* const xc = zbuf + (size_t)kMaxB * K2;
+  float* const xdbl = xc + (size_t)kMaxB * K2;
+  float* const ybuf = xdbl + (size_t)kMaxB * XD;
+  for (int i = threadIdx.x; i < (BMAX - B) * K1; i += kDecThreads) xs[B * K1 + i] = 0.f;   // padded sequences
+  for (int i = threadIdx.x; i < a.n_layers * (int)(sizeof(MambaDecodeLayer) / 8); i += kDecThreads)
+    reinterpret_cast<unsigned long long*>(Ls)[i] = reinterpret_cast<const unsigned long long*>(a.layers)[i];
+  __syncthreads();
 
-  for (int l = 0; l < a.n_layers; ++l) {
-    const MambaDecodeLayer L = a.layers[l];
-    const TW* w_in = static_cast<const TW*>(L.in_proj_weight);
-    // ---- phase 1: norm + in_proj (+ conv step on the x half) ---------------------------------------------------------
-    auto epi1 = [&](int n, int b, float v) {
-      if (n < di) {  // conv branch: shift register + SiLU (simple_mamba.pyc @L233-237 for one position)
-        float* st = L.conv_state + ((size_t)b * di + n) * KC;
-        float acc = L.conv_bias ? L.conv_bias[n] : 0.f;
-        for (int k = 0; k < KC; ++k) {
-          const float sv = (k + 1 < KC) ? st[k + 1] : v;
-          st[k] = sv;
-          acc = fmaf(L.conv_weight[(size_t)n * KC + k], sv, acc);
-        }
-        xc[(size_t)b * di + n] = silu_f(acc);
+  // ---- registers a warp loads ahead of the phase that uses them -------------------------------------------------------------
+  WTile<kRW, KH1> t1[NB1];        // "rows" phases: the ring, holding the head of the warp's first task
+  float4 cst[kRW], cw[kRW];       // conv state / taps of the task's rows for sequence `lane`
+  float cb[kRW];
+  int l = 0;
+  auto conv_pre = [&](int task) {
+    const MambaDecodeLayer& L = Ls[l];
+#pragma unroll
+    for (int r = 0; r < kRW; ++r) {
+      const int n = task * kRW + r;
+      if (n < K2 && lane < B) {
+        cst[r] = *reinterpret_cast<const float4*>(L.conv_state + ((size_t)lane * K2 + n) * 4);
+        cw[r] = __ldg(reinterpret_cast<const float4*>(L.conv_weight + (size_t)n * 4));
+        cb[r] = L.conv_bias ? __ldg(L.conv_bias + n) : 0.f;
+      }
+    }
+  };
+  auto load_first = [&](const TW* W, int nrows) {
+    if (gw * kRW < nrows) {
+#pragma unroll
+      for (int q = 0; q < NB1; ++q) load_chunk<TW, kRW, KH1>(t1[q], W, nrows, K1, gw, q, lane);
+    }
+  };
+  // the warp's first task of a "rows" phase, pulled into L2 two phases ahead (kRW rows x K1 elements, 128 bytes per prefetch)
+  auto prefetch_first = [&](const TW* W, int nrows) {
+    if (gw * kRW < nrows) {
+      const char* p0 = reinterpret_cast<const char*>(W + (size_t)(gw * kRW) * K1);
+      const int bytes = min(kRW, nrows - gw * kRW) * K1 * (int)sizeof(TW);
+      for (int off = lane * 128; off < bytes; off += 32 * 128) prefetch_l2(p0 + off);
+    }
+  };
+  load_first(static_cast<const TW*>(Ls[0].in_proj_weight), 2 * K2);
+  conv_pre(gw);
+
+  for (; l < a.n_layers; ++l) {
+    // ---- phase 1: norm + in_proj (+ conv step on the x half); "rows" mapping ----------------------------------------------
+    stage_norm<TW, K1, BMAX>(xs, red, hidden, resid(l + 1), resid(l), l == 0 ? static_cast<const TW*>(a.embedding) : nullptr, a.token,
+                             Ls[l].norm_weight, a.eps, B);
+    __syncthreads();
+    stamp(10);
+    auto epi1 = [&](int r, int n, int b, float v) {
+      if (n < K2) {  // conv branch: shift register + SiLU (simple_mamba.pyc @L233-237 for one position)
+        const float4 s = cst[r], w = cw[r];
+        *reinterpret_cast<float4*>(Ls[l].conv_state + ((size_t)b * K2 + n) * 4) = make_float4(s.y, s.z, s.w, v);
+        const float acc = fmaf(w.w, v, fmaf(w.z, s.w, fmaf(w.y, s.z, fmaf(w.x, s.y, cb[r]))));
+        xc[(size_t)b * K2 + n] = silu_f(acc);
       } else {
-        zbuf[(size_t)b * di + (n - di)] = v;
+        zbuf[(size_t)b * K2 + (n - K2)] = v;
       }
     };
-    if (dm == 1024) {
-      WTile<TW, 2, 8> t;
-      if (gw * 2 < 2 * di) load_task<TW, 2, 8>(t, w_in, 2 * di, dm, gw, lane);
-      stage_norm<TW, 8>(xs, hidden, resid[(l + 1) & 1], resid[l & 1], l == 0 ? emb : nullptr, a.token, L.norm_weight, a.eps, B, dm);
-      __syncthreads();
-      linear_phase<TW, 2, 8>(t, w_in, static_cast<const TW*>(L.in_proj_bias), 2 * di, dm, B, xs, gw, nwt, lane, epi1);
-    } else {
-      WTile<TW, 1, 1> t;
-      if (gw < 2 * di) load_task<TW, 1, 1>(t, w_in, 2 * di, dm, gw, lane);
-      stage_norm<TW, 1>(xs, hidden, resid[(l + 1) & 1], resid[l & 1], l == 0 ? emb : nullptr, a.token, L.norm_weight, a.eps, B, dm);
-      __syncthreads();
-      linear_phase<TW, 1, 1>(t, w_in, static_cast<const TW*>(L.in_proj_bias), 2 * di, dm, B, xs, gw, nwt, lane, epi1);
-    }
-    prefetch_rows<TW>(static_cast<const TW*>(L.x_proj_weight), XD, di, 1, gw, nwt, lane);
-    stamp();
-    grid_barrier(bar, nblk, gen);
-    stamp();
-    // ---- phase 2: x_proj ------------------------------------------------------------------------------------------------
-    auto epi2 = [&](int n, int b, float v) { xdbl[(size_t)b * XD + n] = v; };
-    const TW* w_x = static_cast<const TW*>(L.x_proj_weight);
-    if (di == 2048) {
-      WTile<TW, 1, 16> t;
-      if (gw < XD) load_task<TW, 1, 16>(t, w_x, XD, di, gw, lane);
-      stage_rows(xs, xc, B, di);                // (every CTA owns at least one of the R + 2N rows: warp 0)
-      __syncthreads();
-      linear_phase<TW, 1, 16>(t, w_x, (const TW*)nullptr, XD, di, B, xs, gw, nwt, lane, epi2);
-    } else {
-      WTile<TW, 1, 2> t;
-      if (gw < XD) load_task<TW, 1, 2>(t, w_x, XD, di, gw, lane);
-      stage_rows(xs, xc, B, di);
-      __syncthreads();
-      linear_phase<TW, 1, 2>(t, w_x, (const TW*)nullptr, XD, di, B, xs, gw, nwt, lane, epi2);
-    }
-    prefetch_rows<TW>(static_cast<const TW*>(L.out_proj_weight), dm, di, 1, gw, nwt, lane);
-    stamp();
-    grid_barrier(bar, nblk, gen);
-    stamp();
-    // ---- phase 3: dt_proj + softplus + SSM step + D skip + gate; a half-warp per (b, d) ------------------------------------
+    rows_phase<TW, kRW, KH1, NQ1, NB1, BMAX>(t1, static_cast<const TW*>(Ls[l].in_proj_weight), static_cast<const TW*>(Ls[l].in_proj_bias),
+                                             2 * K2, K1, B, xs, gw, nwt, lane, conv_pre, epi1, [&]() { stamp(11); });
+    stamp(1);
+    grid_arrive(a.barrier);
+    target += nblk;
+    // ---- phase 2: x_proj; K-split mapping ------------------------------------------------------------------------------------
+    prefetch_rows_l2<TW, KQ>(static_cast<const TW*>(Ls[l].x_proj_weight), XD, K2, 2, warp, lane);
+    prefetch_rows_l2<TW, KQ>(static_cast<const TW*>(Ls[l].out_proj_weight), K1, K2, RMAX4, warp, lane);
+    grid_wait(a.barrier, target);
+    stamp(2);
+    ksplit_rows<TW, 2, KQ, KP, NP, BH, BMAX, 8>(static_cast<const TW*>(Ls[l].x_proj_weight), XD, K2, xc, B, red, warp, kq, bq);
+    finish_rows<TW, BMAX, 8>(red, (const TW*)nullptr, XD, B, 2, [&](int n, int b, float v) { xdbl[(size_t)b * XD + n] = v; });
+    stamp(3);
+    grid_arrive(a.barrier);
+    target += nblk;
+    // ---- phase 3: dt_proj + softplus + SSM step + D skip + gate; a half-warp per (channel, batch parity) ---------------------
     {
-      const int hl = threadIdx.x & 15;
-      const unsigned mask = 0xffffu << (threadIdx.x & 16);
-      const int64_t items = (int64_t)B * di;
-      const int64_t hw0 = ((int64_t)(threadIdx.x >> 4)) * nblk + blockIdx.x, nhw = (int64_t)nblk * (kDecThreads >> 4);
-      for (int64_t item = hw0; item < items; item += nhw) {
-        const int b = (int)(item / di), d = (int)(item - (int64_t)b * di);
-        float dot = 0.f;
-        const float* wdt = L.dt_weight + (size_t)d * R;
-        const float* xd = xdbl + (size_t)b * XD;
-        for (int r4 = hl; r4 < (R >> 2); r4 += 16) {
-          const float4 wv = __ldg(reinterpret_cast<const float4*>(wdt) + r4);
-          const float4 xv = ldcg4(xd + 4 * r4);
-          dot = fmaf(wv.x, xv.x, fmaf(wv.y, xv.y, fmaf(wv.z, xv.z, fmaf(wv.w, xv.w, dot))));
-        }
+      const MambaDecodeLayer& L = Ls[l];
+      const int hl = lane & 15;
+      const unsigned mask = 0xffffu << (lane & 16);
+      const int hw0 = (threadIdx.x >> 4) * nblk + blockIdx.x, nhw = nblk * (kDecThreads >> 4);
+      const bool nact = hl < (N >> 2), ract = hl < (R >> 2);
+      const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      SsmPre<BH> sp[NI];
+      auto ssm_pre = [&](SsmPre<BH>& s, int item) {
+        const int d = item >> 1, p = item & 1;
+        s.A4 = nact ? __ldg(reinterpret_cast<const float4*>(L.A + (size_t)d * N) + hl) : z4;
+        s.w4 = ract ? __ldg(reinterpret_cast<const float4*>(L.dt_weight + (size_t)d * R) + hl) : z4;
+        s.dtb = L.dt_bias ? __ldg(L.dt_bias + d) : 0.f;
+        s.Dd = L.D ? __ldg(L.D + d) : 0.f;
 #pragma unroll
-        for (int o = 8; o > 0; o >>= 1) dot += __shfl_xor_sync(mask, dot, o);
-        dot += L.dt_bias ? L.dt_bias[d] : 0.f;
-        const float delta = softplus_fast(dot);
-        const float xcv = ldcg(xc + (size_t)b * di + d);
-        const float du = delta * xcv, dl2 = delta * kLog2e;
-        float* h = L.ssm_state + ((size_t)b * di + d) * N;
-        const float* A = L.A + (size_t)d * N;
-        float y = 0.f;
-        for (int n4 = hl; n4 < (N >> 2); n4 += 16) {
-          const float4 a4 = __ldg(reinterpret_cast<const float4*>(A) + n4);
-          float4 h4 = reinterpret_cast<float4*>(h)[n4];
-          const float4 bb = ldcg4(xd + R + 4 * n4), cc = ldcg4(xd + R + N + 4 * n4);
-          h4.x = fmaf(ex2_approx(dl2 * a4.x), h4.x, du * bb.x);
-          h4.y = fmaf(ex2_approx(dl2 * a4.y), h4.y, du * bb.y);
-          h4.z = fmaf(ex2_approx(dl2 * a4.z), h4.z, du * bb.z);
-          h4.w = fmaf(ex2_approx(dl2 * a4.w), h4.w, du * bb.w);
-          reinterpret_cast<float4*>(h)[n4] = h4;
-          y = fmaf(h4.x, cc.x, fmaf(h4.y, cc.y, fmaf(h4.z, cc.z, fmaf(h4.w, cc.w, y))));
+        for (int i = 0; i < BH; ++i) {
+          const int b = min(p + 2 * i, B - 1);   // (padded sequences repeat the last one; nothing of theirs is stored)
+          s.h[i] = nact ? *(reinterpret_cast<const float4*>(L.ssm_state + ((size_t)b * K2 + d) * N) + hl) : z4;
         }
+      };
+      // before the barrier opens: the items' state rows, A and dt_proj rows on their way into L2
 #pragma unroll
-        for (int o = 8; o > 0; o >>= 1) y += __shfl_xor_sync(mask, y, o);
-        if (hl == 0) {
-          y = fmaf(L.D ? L.D[d] : 0.f, xcv, y);
-          y *= silu_fast(ldcg(zbuf + (size_t)b * di + d));
-          ybuf[(size_t)b * di + d] = y;
+      for (int k = 0; k < NI; ++k) {
+        const int item = hw0 + k * nhw;
+        if (item < 2 * K2) {
+          const int d = item >> 1, b = (item & 1) + 2 * hl;
+          const int nb = (N * 4 + 127) >> 7;   // 128-byte lines per row
+          if (b < B)
+            for (int c = 0; c < nb; ++c) prefetch_l2(reinterpret_cast<const char*>(L.ssm_state + ((size_t)b * K2 + d) * N) + c * 128);
+          if (hl == 15) prefetch_l2(L.A + (size_t)d * N), prefetch_l2(L.dt_weight + (size_t)d * R);
+          if (hl == 14 && N * 4 > 128) prefetch_l2(L.A + (size_t)d * N + 32);
+          if (hl == 13 && R * 4 > 128) prefetch_l2(L.dt_weight + (size_t)d * R + 32);
         }
       }
-    }
-    stamp();
-    grid_barrier(bar, nblk, gen);
-    stamp();
-    // ---- phase 4: out_proj -----------------------------------------------------------------------------------------------
-    auto epi4 = [&](int n, int b, float v) { hidden[(size_t)b * dm + n] = v; };
-    const TW* w_o = static_cast<const TW*>(L.out_proj_weight);
-    if (di == 2048) {
-      WTile<TW, 1, 16> t;
-      if (gw < dm) load_task<TW, 1, 16>(t, w_o, dm, di, gw, lane);
-      stage_rows(xs, ybuf, B, di);
+      if (l + 1 < a.n_layers)
+        prefetch_first(static_cast<const TW*>(Ls[l + 1].in_proj_weight), 2 * K2);
+      else
+        prefetch_first(static_cast<const TW*>(a.head_weight), a.vocab);
+      grid_wait(a.barrier, target);
+      stamp(4);
+      // x_proj's output of every sequence -> shared memory (one L2 round trip for the CTA); the first item's state rows
+      // and gate inputs -> registers
+      for (int i = threadIdx.x; i < (B * XD) >> 2; i += kDecThreads) reinterpret_cast<float4*>(xd_s)[i] = ldcg4(xdbl + 4 * i);
+      float xcv[NI][BH], zv[NI][BH];
+      auto gate_pre = [&](float (&xv)[BH], float (&zz)[BH], int item) {
+#pragma unroll
+        for (int i = 0; i < BH; ++i) {
+          const int b = min((item & 1) + 2 * i, B - 1);
+          xv[i] = ldcg(xc + (size_t)b * K2 + (item >> 1)), zz[i] = ldcg(zbuf + (size_t)b * K2 + (item >> 1));
+        }
+      };
+      if (hw0 < 2 * K2) ssm_pre(sp[0], hw0), gate_pre(xcv[0], zv[0], hw0);
       __syncthreads();
-      linear_phase<TW, 1, 16>(t, w_o, static_cast<const TW*>(L.out_proj_bias), dm, di, B, xs, gw, nwt, lane, epi4);
+      stamp(12);
+      // one item: BH independent sequences, no branches inside (the chains of the sequences interleave)
+      auto ssm_item = [&](const SsmPre<BH>& s, const float (&xv)[BH], const float (&zz)[BH], int item) {
+        const int d = item >> 1, p = item & 1;
+#pragma unroll
+        for (int i = 0; i < BH; ++i) {
+          const int b = p + 2 * i, bc = min(b, B - 1);
+          const float* xd = xd_s + bc * XD;
+          const float4 xdt = ract ? *reinterpret_cast<const float4*>(xd + 4 * hl) : z4;
+          const float4 bb = nact ? *reinterpret_cast<const float4*>(xd + R + 4 * hl) : z4;
+          const float4 cc = nact ? *reinterpret_cast<const float4*>(xd + R + N + 4 * hl) : z4;
+          float dot = fmaf(s.w4.x, xdt.x, fmaf(s.w4.y, xdt.y, fmaf(s.w4.z, xdt.z, s.w4.w * xdt.w)));
+#pragma unroll
+          for (int o = 8; o > 0; o >>= 1) dot += __shfl_xor_sync(mask, dot, o);
+          const float delta = softplus_fast(dot + s.dtb);
+          const float du = delta * xv[i], dl2 = delta * kLog2e;
+          float4 h4 = s.h[i];
+          h4.x = fmaf(ex2_approx(dl2 * s.A4.x), h4.x, du * bb.x);
+          h4.y = fmaf(ex2_approx(dl2 * s.A4.y), h4.y, du * bb.y);
+          h4.z = fmaf(ex2_approx(dl2 * s.A4.z), h4.z, du * bb.z);
+          h4.w = fmaf(ex2_approx(dl2 * s.A4.w), h4.w, du * bb.w);
+          if (nact && b < B) *(reinterpret_cast<float4*>(L.ssm_state + ((size_t)b * K2 + d) * N) + hl) = h4;
+          float y = fmaf(h4.x, cc.x, fmaf(h4.y, cc.y, fmaf(h4.z, cc.z, h4.w * cc.w)));
+#pragma unroll
+          for (int o = 8; o > 0; o >>= 1) y += __shfl_xor_sync(mask, y, o);
+          if (hl == 0 && b < B) ybuf[(size_t)b * K2 + d] = fmaf(s.Dd, xv[i], y) * silu_fast(zz[i]);
+        }
+      };
+      static_assert(NI == 2, "two register sets: the next item loads while this one is computed");
+      for (int item = hw0; item < 2 * K2; item += 2 * nhw) {
+        const int nxt = item + nhw;
+        if (item != hw0) ssm_pre(sp[0], item), gate_pre(xcv[0], zv[0], item);
+        if (nxt < 2 * K2) ssm_pre(sp[1], nxt), gate_pre(xcv[1], zv[1], nxt);
+        ssm_item(sp[0], xcv[0], zv[0], item);
+        if (nxt < 2 * K2) ssm_item(sp[1], xcv[1], zv[1], nxt);
+      }
+    }
+    stamp(5);
+    grid_arrive(a.barrier);
+    target += nblk;
+    // ---- phase 4: out_proj; K-split mapping ------------------------------------------------------------------------------------
+    grid_wait(a.barrier, target);
+    stamp(6);
+    ksplit_rows<TW, RMAX4, KQ, KP, NP, BH, BMAX, 8>(static_cast<const TW*>(Ls[l].out_proj_weight), K1, K2, ybuf, B, red, warp, kq, bq);
+    stamp(14);
+    finish_rows<TW, BMAX, 8>(red, static_cast<const TW*>(Ls[l].out_proj_bias), K1, B, RMAX4, [&](int n, int b, float v) { hidden[(size_t)b * K1 + n] = v; });
+    stamp(7);
+    grid_arrive(a.barrier);
+    target += nblk;
+    if (l + 1 < a.n_layers) {
+      ++l;   // conv_pre reads the NEXT layer's descriptor
+      load_first(static_cast<const TW*>(Ls[l].in_proj_weight), 2 * K2);
+      conv_pre(gw);
+      --l;
     } else {
-      WTile<TW, 1, 2> t;
-      if (gw < dm) load_task<TW, 1, 2>(t, w_o, dm, di, gw, lane);
-      stage_rows(xs, ybuf, B, di);
-      __syncthreads();
-      linear_phase<TW, 1, 2>(t, w_o, static_cast<const TW*>(L.out_proj_bias), dm, di, B, xs, gw, nwt, lane, epi4);
+      load_first(static_cast<const TW*>(a.head_weight), a.vocab);
     }
-    if (l + 1 < a.n_layers)
-      prefetch_rows<TW>(static_cast<const TW*>(a.layers[l + 1].in_proj_weight), 2 * di, dm, dm == 1024 ? 2 : 1, gw, nwt, lane);
-    else
-      prefetch_rows<TW>(static_cast<const TW*>(a.head_weight), a.vocab, dm, dm == 1024 ? 2 : 1, gw, nwt, lane);
-    stamp();
-    grid_barrier(bar, nblk, gen);
-    stamp();
+    grid_wait(a.barrier, target);
+    stamp(8);
   }
-  // ---- final norm + LM head ----------------------------------------------------------------------------------------------
-  auto epih = [&](int n, int b, float v) { a.logits[(size_t)b * a.logits_bs + n] = v; };
-  const TW* w_h = static_cast<const TW*>(a.head_weight);
-  if (dm == 1024) {
-    WTile<TW, 2, 8> t;
-    if (gw * 2 < a.vocab) load_task<TW, 2, 8>(t, w_h, a.vocab, dm, gw, lane);
-    stage_norm<TW, 8>(xs, hidden, resid[(a.n_layers + 1) & 1], nullptr, (const TW*)nullptr, a.token, a.norm_f_weight, a.eps, B, dm);
-    __syncthreads();
-    linear_phase<TW, 2, 8>(t, w_h, static_cast<const TW*>(a.head_bias), a.vocab, dm, B, xs, gw, nwt, lane, epih);
-  } else {
-    WTile<TW, 1, 1> t;
-    if (gw < a.vocab) load_task<TW, 1, 1>(t, w_h, a.vocab, dm, gw, lane);
-    stage_norm<TW, 1>(xs, hidden, resid[(a.n_layers + 1) & 1], nullptr, (const TW*)nullptr, a.token, a.norm_f_weight, a.eps, B, dm);
-    __syncthreads();
-    linear_phase<TW, 1, 1>(t, w_h, static_cast<const TW*>(a.head_bias), a.vocab, dm, B, xs, gw, nwt, lane, epih);
+  // ---- final norm + LM head; "rows" mapping ------------------------------------------------------------------------------------
+  stage_norm<TW, K1, BMAX>(xs, red, hidden, resid(a.n_layers + 1), nullptr, (const TW*)nullptr, a.token, a.norm_f_weight, a.eps, B);
+  __syncthreads();
+  rows_phase<TW, kRW, KH1, NQ1, NB1, BMAX>(t1, static_cast<const TW*>(a.head_weight), static_cast<const TW*>(a.head_bias), a.vocab, K1, B,
+                                           xs, gw, nwt, lane, [](int) {}, [&](int, int n, int b, float v) { a.logits[(size_t)b * a.logits_bs + n] = v; }, []() {});
+  stamp(9);
+}
+
+template <typename TW, int BMAX, bool BIG>
+int launch_decode(const MambaDecodeTokenArgs& a, cudaLaunchConfig_t& cfg) {
+  static thread_local SmemConfig sc;
+  auto kern = decode_token_kernel<TW, BMAX, BIG>;
+  if (int rc = ensure_dynamic_smem(kern, cfg.dynamicSmemBytes, sc, "decode_token")) return rc;
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    return set_error(MAMBA_ELAUNCH, "decode_token: %s", cudaGetErrorString(e));
   }
-  stamp();
+  return MAMBA_OK;
+}
+template <typename TW, bool BIG>
+int launch_decode_b(const MambaDecodeTokenArgs& a, cudaLaunchConfig_t& cfg, int bmax) {
+#ifdef MB_DEC_DEV   // development builds: one batch size per shape
+  (void)bmax;
+  return launch_decode<TW, BIG ? 10 : 6, BIG>(a, cfg);
+#else
+  switch (bmax) {
+    case 2: return launch_decode<TW, 2, BIG>(a, cfg);
+    case 4: return launch_decode<TW, 4, BIG>(a, cfg);
+    case 6: return launch_decode<TW, 6, BIG>(a, cfg);
+    case 8: return launch_decode<TW, 8, BIG>(a, cfg);
+    case 10: return launch_decode<TW, 10, BIG>(a, cfg);
+    case 12: return launch_decode<TW, 12, BIG>(a, cfg);
+    case 14: return launch_decode<TW, 14, BIG>(a, cfg);
+    default: return launch_decode<TW, 16, BIG>(a, cfg);
+  }
+#endif
 }
 
 }  // namespace
@@ -391,6 +590,11 @@ extern "C" size_t mamba_decode_token_scratch_bytes(int d_model, int d_inner, int
   return sizeof(float) * (size_t)mb::kMaxB * (3 * (size_t)d_model + 3 * (size_t)d_inner + dt_rank + 2 * d_state) + 256;
 }
 
+extern "C" size_t mamba_decode_token_barrier_bytes(int n_layers) {
+  if (n_layers <= 0) return 0;
+  return sizeof(unsigned int) * mb::kStampWords + sizeof(unsigned long long) * (size_t)(16 * n_layers + 8);
+}
+
 extern "C" int mamba_decode_token(const MambaDecodeTokenArgs* a, void* stream) {
   using namespace mb;
   if (!a || a->struct_size != (int32_t)sizeof(MambaDecodeTokenArgs))
@@ -400,18 +604,23 @@ extern "C" int mamba_decode_token(const MambaDecodeTokenArgs* a, void* stream) {
       !a->scratch || !a->barrier)
     return set_error(MAMBA_EINVAL, "decode_token: null pointer");
   // supported shapes: (d_model, d_inner) = (1024, 2048) [the repo's model] or (128, 256) [the tests' small model];
-  // d_state and dt_rank multiples of 4
+  // d_state and dt_rank multiples of 4 up to 64, d_conv 4
   const bool big = a->d_model == 1024 && a->d_inner == 2048, small = a->d_model == 128 && a->d_inner == 256;
-  if (!(big || small) || a->d_state % 4 || a->dt_rank % 4 || a->d_conv < 1 || a->d_conv > 8)
-    return set_error(MAMBA_ESIZE, "decode_token: unsupported shape d_model %d d_inner %d d_state %d dt_rank %d", a->d_model,
-                     a->d_inner, a->d_state, a->dt_rank);
+  if (!(big || small) || a->d_state % 4 || a->dt_rank % 4 || a->d_state > 64 || a->dt_rank > 64 || a->d_conv != 4)
+    return set_error(MAMBA_ESIZE, "decode_token: unsupported shape d_model %d d_inner %d d_state %d dt_rank %d d_conv %d", a->d_model,
+                     a->d_inner, a->d_state, a->dt_rank, a->d_conv);
   if (a->scratch_bytes < mamba_decode_token_scratch_bytes(a->d_model, a->d_inner, a->d_state, a->dt_rank))
     return set_error(MAMBA_ESIZE, "decode_token: scratch too small");
   if (a->w_dtype != MAMBA_F32 && a->w_dtype != MAMBA_BF16) return set_error(MAMBA_EDTYPE, "decode_token: w_dtype %d", a->w_dtype);
-  const size_t smem = sizeof(float) * (size_t)a->batch * (size_t)(a->d_inner > a->d_model ? a->d_inner : a->d_model);
   int dev = 0, nsm = kNumSMs;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+  // rows per CTA of the K-split phases are compile-time: x_proj <= 2, out_proj <= 7 (1)
+  if (a->dt_rank + 2 * a->d_state > 2 * nsm || a->d_model > (big ? 7 : 1) * nsm)
+    return set_error(MAMBA_ESIZE, "decode_token: %d SMs are too few for this shape", nsm);
+  const int bmax = (a->batch + 1) & ~1;
+  const size_t smem = sizeof(float) * ((size_t)bmax * a->d_model + (size_t)kDecWarps * 8 * bmax + (size_t)bmax * 192) +
+                      sizeof(MambaDecodeLayer) * (size_t)a->n_layers;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(nsm), cfg.blockDim = dim3(kDecThreads), cfg.dynamicSmemBytes = smem;
   cfg.stream = static_cast<cudaStream_t>(stream);
@@ -419,21 +628,14 @@ extern "C" int mamba_decode_token(const MambaDecodeTokenArgs* a, void* stream) {
   attr[0].id = cudaLaunchAttributeCooperative;   // every CTA resident at once: the grid barrier cannot deadlock
   attr[0].val.cooperative = 1;
   cfg.attrs = attr, cfg.numAttrs = 1;
-  cudaError_t e = cudaMemsetAsync(a->barrier, 0, 2 * sizeof(unsigned int), cfg.stream);   // grid-barrier state
+  cudaError_t e = cudaMemsetAsync(a->barrier, 0, sizeof(unsigned int), cfg.stream);   // the arrival counter
   if (e != cudaSuccess) return set_error(MAMBA_ELAUNCH, "decode_token: memset: %s", cudaGetErrorString(e));
-  if (a->w_dtype == MAMBA_F32) {
-    static thread_local SmemConfig c32;
-    if (int rc = ensure_dynamic_smem(decode_token_kernel<float>, smem, c32, "decode_token")) return rc;
-    e = cudaLaunchKernelEx(&cfg, decode_token_kernel<float>, *a);
-  } else {
-    static thread_local SmemConfig c16;
-    if (int rc = ensure_dynamic_smem(decode_token_kernel<__nv_bfloat16>, smem, c16, "decode_token")) return rc;
-    e = cudaLaunchKernelEx(&cfg, decode_token_kernel<__nv_bfloat16>, *a);
-  }
-  if (e != cudaSuccess) {
-    (void)cudaGetLastError();
-    return set_error(MAMBA_ELAUNCH, "decode_token: %s", cudaGetErrorString(e));
-  }
+  int rc;
+  if (a->w_dtype == MAMBA_F32)
+    rc = big ? launch_decode_b<float, true>(*a, cfg, bmax) : launch_decode_b<float, false>(*a, cfg, bmax);
+  else
+    rc = big ? launch_decode_b<__nv_bfloat16, true>(*a, cfg, bmax) : launch_decode_b<__nv_bfloat16, false>(*a, cfg, bmax);
+  if (rc != MAMBA_OK) return rc;
   count_launch();
   return check_launch("decode_token");
 }

@@ -708,7 +708,7 @@ class DecodeTokenPlan:
         w = model.layers[0].mixer.in_proj.weight
         return ((p.d_model, p.d_inner) in DecodeTokenPlan.SHAPES and p.d_state % 4 == 0 and p.dt_rank % 4 == 0 and w.is_cuda
                 and w.dtype == torch.float32 and all(cs.dtype == torch.float32 for cs, _ in cache)
-                and model.lm_head.bias is None)
+                and model.lm_head.bias is None and p.d_state <= 64 and p.dt_rank <= 64 and p.d_conv == 4)
 
     def __init__(self, model, cache, token, logits, weight_dtype=None):
         p = model.params
@@ -747,7 +747,7 @@ class DecodeTokenPlan:
         self.layers_dev = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
         n = lib().mamba_decode_token_scratch_bytes(p.d_model, p.d_inner, p.d_state, p.dt_rank)
         self.scratch = torch.zeros(n, dtype=torch.uint8, device=dev)
-        self.barrier = torch.zeros(2, dtype=torch.int32, device=dev)
+        self.barrier = torch.zeros(lib().mamba_decode_token_barrier_bytes(len(model.layers)), dtype=torch.uint8, device=dev)
         self.token, self.logits = token, logits
         a = DecodeTokenArgs()
         a.struct_size = ct.sizeof(DecodeTokenArgs)

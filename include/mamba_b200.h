@@ -314,9 +314,14 @@ int mamba_sample_step(const MambaSampleStepArgs* args, void* stream);
  * mamba_linear_step, mamba_ssm_step) become one cooperative grid (one CTA per SM) with a grid barrier between phases.
  * `layers` is a DEVICE array of n_layers descriptors; `token` [B] int64 is read on the device (it is the sampler's
  * output of the previous step); `logits` [B, vocab] fp32 feeds mamba_sample_step.  conv_state / ssm_state are updated
- * in place.  `scratch` (mamba_decode_token_scratch_bytes) and `barrier` (2 x uint32) are caller-owned.
- * Supported shapes: (d_model, d_inner) = (1024, 2048) or (128, 256); d_state % 4 == 0, dt_rank % 4 == 0.
+ * in place.  `scratch` (mamba_decode_token_scratch_bytes) and `barrier` (mamba_decode_token_barrier_bytes: the arrival
+ * counter of the grid barrier, which the call zeroes, followed by room for time stamps) are caller-owned.
+ * With MAMBA_DECODE_FLAG_STAMPS thread 0 of CTA 0 appends (event id << 56 | %globaltimer ns) as uint64 from byte 16 of
+ * `barrier`: id 0 at kernel start; per layer 1..8 (end of phase / barrier open, for the 4 phases) and 10..14 inside the
+ * phases; 9 at the end of the head (at most 16*n_layers + 8 values).
+ * Supported shapes: (d_model, d_inner) = (1024, 2048) or (128, 256); d_state, dt_rank multiples of 4 up to 64; d_conv 4.
  * ------------------------------------------------------------------------------------------ */
+#define MAMBA_DECODE_FLAG_STAMPS 1
 typedef struct MambaDecodeLayer {
   const float* norm_weight;       /* [d_model] RMSNorm of the residual block                 */
   const void* in_proj_weight;     /* [2*d_inner, d_model]  (w_dtype)                         */
@@ -340,7 +345,7 @@ typedef struct MambaDecodeTokenArgs {
   int32_t batch, n_layers, vocab;
   int32_t d_model, d_inner, d_state, dt_rank, d_conv;
   float eps;
-  int32_t reserved;
+  int32_t flags;                  /* MAMBA_DECODE_FLAG_*                                      */
   const int64_t* token;           /* [B] the token each sequence consumes                    */
   const void* embedding;          /* [vocab, d_model]  (w_dtype)                              */
   const MambaDecodeLayer* layers; /* DEVICE array [n_layers]                                  */
@@ -349,10 +354,11 @@ typedef struct MambaDecodeTokenArgs {
   const void* head_bias;          /* [vocab] or NULL                                          */
   float* logits;  int64_t logits_bs;  /* [B, vocab] fp32                                      */
   float* scratch; size_t scratch_bytes;
-  unsigned int* barrier;          /* 2 x uint32, any contents                                 */
+  unsigned int* barrier;          /* mamba_decode_token_barrier_bytes(n_layers), any contents */
 } MambaDecodeTokenArgs;
 
 size_t mamba_decode_token_scratch_bytes(int d_model, int d_inner, int d_state, int dt_rank);
+size_t mamba_decode_token_barrier_bytes(int n_layers);
 int mamba_decode_token(const MambaDecodeTokenArgs* args, void* stream);
 
 /* ------------------------------------------------------------------------------------------
