@@ -106,12 +106,89 @@ __device__ __forceinline__ void mul_chunk(const WTile<RW, KH>& t, const float* x
     }
   }
 }
+// Sum NV values over the 32 lanes with NV - 1 + ... shuffles instead of 5 per value: at every step a lane keeps one half
+// of its values and sends the other half to its partner (NV -> ceil(NV/2) -> ...).  Afterwards lane L holds, in
+// v[0 .. NF), the totals of the values rs_index<NV>(L, j) (or nothing, if that index is >= NV).
+template <int NV>
+struct RsPlan {
+  static constexpr int n1 = (NV + 1) / 2, n2 = (n1 + 1) / 2, n3 = (n2 + 1) / 2, n4 = (n3 + 1) / 2, n5 = (n4 + 1) / 2;
+  static constexpr int NF = n5;
+};
+template <int N, int O>
+__device__ __forceinline__ void rs_step(float* v, int lane) {
+  constexpr int H = (N + 1) / 2;
+  const bool up = lane & O;
+#pragma unroll
+  for (int j = 0; j < H; ++j) {
+    const float lo = v[j], hi = (j + H < N) ? v[j + H] : 0.f;
+    const float send = up ? lo : hi, keep = up ? hi : lo;
+    v[j] = keep + __shfl_xor_sync(0xffffffffu, send, O);
+  }
+}
+template <int NV>
+__device__ __forceinline__ void reduce_scatter(float (&v)[NV], int lane) {
+  using P = RsPlan<NV>;
+  rs_step<NV, 16>(v, lane);
+  rs_step<P::n1, 8>(v, lane);
+  rs_step<P::n2, 4>(v, lane);
+  rs_step<P::n3, 2>(v, lane);
+  rs_step<P::n4, 1>(v, lane);
+}
+// index of the value whose total lane `lane` holds in slot j (>= NV: none)
+template <int NV>
+__device__ __forceinline__ int rs_index(int lane, int j) {
+  using P = RsPlan<NV>;
+  int i = j;                                   // position among the n5 values after the last step
+  bool ok = true;
+  if (lane & 1) i += P::n5;
+  ok = ok && i < P::n4;
+  if (lane & 2) i += P::n4;
+  ok = ok && i < P::n3;
+  if (lane & 4) i += P::n3;
+  ok = ok && i < P::n2;
+  if (lane & 8) i += P::n2;
+  ok = ok && i < P::n1;
+  if (lane & 16) i += P::n1;
+  return (ok && i < NV) ? i : NV;
+}
+
+// the same over the 16 lanes of a half-warp (offsets 8, 4, 2, 1): NV -> ... -> RsPlan16<NV>::NF values per lane
+template <int NV>
+struct RsPlan16 {
+  static constexpr int n1 = (NV + 1) / 2, n2 = (n1 + 1) / 2, n3 = (n2 + 1) / 2, n4 = (n3 + 1) / 2;
+  static constexpr int NF = n4;
+};
+template <int NV>
+__device__ __forceinline__ void reduce_scatter16(float (&v)[NV], int lane) {
+  using P = RsPlan16<NV>;
+  rs_step<NV, 8>(v, lane);
+  rs_step<P::n1, 4>(v, lane);
+  rs_step<P::n2, 2>(v, lane);
+  rs_step<P::n3, 1>(v, lane);
+}
+template <int NV>
+__device__ __forceinline__ int rs_index16(int lane, int j) {
+  using P = RsPlan16<NV>;
+  int i = j;
+  bool ok = true;
+  if (lane & 1) i += P::n4;
+  ok = ok && i < P::n3;
+  if (lane & 2) i += P::n3;
+  ok = ok && i < P::n2;
+  if (lane & 4) i += P::n2;
+  ok = ok && i < P::n1;
+  if (lane & 8) i += P::n1;
+  return (ok && i < NV) ? i : NV;
+}
+
 // One "rows" phase.  The first NB chunks of the warp's first task are loaded by the caller (before the grid barrier
-// opens); pre(task) issues a task's other independent loads, epi(r, n, b, value) is called by lane b of the owning warp.
+// opens); pre(task) issues a task's other independent loads, epi(slot, r, n, b, value) is called by the lane that holds
+// the total of (row r, sequence b) after the reduce-scatter (slot = rs slot of that lane).
 template <typename TW, int RW, int KH, int NQ, int NB, int BMAX, typename Pre, typename Epi, typename Mark>
 __device__ __forceinline__ void rows_phase(WTile<RW, KH> (&t)[NB], const TW* __restrict__ W, const TW* __restrict__ bias, int N, int K,
                                            int B, const float* xs, int gw, int nwt, int lane, Pre pre, Epi epi, Mark mark) {
   static_assert(NQ % NB == 0, "the ring position of a chunk must not depend on the task");
+  constexpr int NV = RW * BMAX;
   for (int task = gw; task * RW < N; task += nwt) {
     if (task != gw) pre(task);
     const int nxt = task + nwt;
@@ -134,18 +211,17 @@ __device__ __forceinline__ void rows_phase(WTile<RW, KH> (&t)[NB], const TW* __r
       }
     }
     mark();
+    float v[NV];
 #pragma unroll
-    for (int r = 0; r < RW; ++r) {
-      float mine = 0.f;
+    for (int r = 0; r < RW; ++r)
 #pragma unroll
-      for (int b = 0; b < BMAX; ++b) {
-        float v = acc[r][b].x + acc[r][b].y;
+      for (int b = 0; b < BMAX; ++b) v[r * BMAX + b] = acc[r][b].x + acc[r][b].y;
+    reduce_scatter<NV>(v, lane);
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == b) mine = v;
-      }
-      const int n = task * RW + r;
-      if (n < N && lane < B) epi(r, n, lane, mine + (bias ? IO<TW>::ld(bias + n) : 0.f));
+    for (int j = 0; j < RsPlan<NV>::NF; ++j) {
+      const int i = rs_index<NV>(lane, j);
+      const int r = i / BMAX, b = i - r * BMAX, n = task * RW + r;
+      if (i < NV && n < N && b < B) epi(j, r, n, b, v[j] + (bias ? IO<TW>::ld(bias + n) : 0.f));
     }
   }
 }
@@ -205,15 +281,21 @@ __device__ __forceinline__ void ksplit_rows(const TW* __restrict__ W, int N, int
 #pragma unroll
         for (int j = 0; j < KP; ++j) acc[r][i] = dot4(w[r][j], x[i][j], acc[r][i]);
   }
+  // reduce over the 16 K-lanes of each batch-parity half: RG*BH values, reduce-scatter (one shuffle per value and step
+  // on half as many values each step)
+  constexpr int NV = RG * BH;
+  float v[NV];
 #pragma unroll
   for (int r = 0; r < RG; ++r)
 #pragma unroll
-    for (int i = 0; i < BH; ++i) {
-      float v = acc[r][i];
+    for (int i = 0; i < BH; ++i) v[r * BH + i] = acc[r][i];
+  reduce_scatter16<NV>(v, kq);
 #pragma unroll
-      for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (kq == 0) red[(warp * RMAX + r) * BMAX + bq + 2 * i] = v;
-    }
+  for (int j = 0; j < RsPlan16<NV>::NF; ++j) {
+    const int idx = rs_index16<NV>(kq, j);
+    const int r = idx / BH, i = idx - r * BH;
+    if (idx < NV) red[(warp * RMAX + r) * BMAX + bq + 2 * i] = v[j];
+  }
 }
 // fixed-order sum over the warps; thread (j, b) owns output row blockIdx + j*gridDim of sequence b
 template <typename TW, int BMAX, int RMAX, typename Epi>
@@ -229,13 +311,14 @@ __device__ __forceinline__ void finish_rows(const float* red, const TW* __restri
   }
 }
 
-// stage s = hidden + resid (or the embedding rows for the first layer), write s as the new residual (CTA 0), and leave
-// rmsnorm(s) * w in shared memory:  `normed, resid = norm(hidden, resid)`  (simple_mamba.pyc @L179 / @L346).
+// RMSNorm of the residual stream into shared memory:  `normed, resid = norm(hidden, resid)`  (simple_mamba.pyc @L179 /
+// @L346).  The stream S = hidden + resid is kept in global memory by out_proj's epilogue (which adds its result in
+// place); the first layer reads the embedding rows instead and CTA 0 writes them out as S.
 // Thread t owns the 16-byte column pieces t, t + 256, ... of EVERY sequence: all of the CTA's loads are in flight
 // together (one L2 round trip), the per-sequence sums of squares meet in shared memory (fixed order).
 template <typename TW, int K, int BMAX>
-__device__ __forceinline__ void stage_norm(float* xs, float* ssq, const float* hidden, const float* resid_in, float* resid_out,
-                                           const TW* emb, const int64_t* tok, const float* norm_w, float eps, int B) {
+__device__ __forceinline__ void stage_norm(float* xs, float* ssq, float* S, const TW* emb, const int64_t* tok, const float* norm_w,
+                                           float eps, int B) {
   constexpr int C4 = K / 4;                                              // 16-byte pieces per row
   constexpr int NC = (C4 + kDecThreads - 1) / kDecThreads;              // ... per thread and row (1)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -244,43 +327,34 @@ __device__ __forceinline__ void stage_norm(float* xs, float* ssq, const float* h
     const int col = threadIdx.x + c * kDecThreads;
     const bool on = col < C4;
     float4 v[BMAX];
-    if (emb != nullptr) {
 #pragma unroll
-      for (int b = 0; b < BMAX; ++b) {
-        float e[4] = {0.f, 0.f, 0.f, 0.f};
-        if (on && b < B) ldw4<TW>(emb + (size_t)tok[b] * K + 4 * col, e);
-        v[b] = make_float4(e[0], e[1], e[2], e[3]);
+    for (int b = 0; b < BMAX; ++b) {
+      v[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (on && b < B) {
+        if (emb != nullptr) {
+          float e[4];
+          ldw4<TW>(emb + (size_t)tok[b] * K + 4 * col, e);
+          v[b] = make_float4(e[0], e[1], e[2], e[3]);
+        } else {
+          v[b] = ldcg4(S + (size_t)b * K + 4 * col);
+        }
       }
-    } else {
-      float4 r[BMAX];
-#pragma unroll
-      for (int b = 0; b < BMAX; ++b) {
-        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        v[b] = (on && b < B) ? ldcg4(hidden + (size_t)b * K + 4 * col) : z4;
-        r[b] = (on && b < B) ? ldcg4(resid_in + (size_t)b * K + 4 * col) : z4;
-      }
-#pragma unroll
-      for (int b = 0; b < BMAX; ++b) v[b] = make_float4(v[b].x + r[b].x, v[b].y + r[b].y, v[b].z + r[b].z, v[b].w + r[b].w);
     }
     float ss[BMAX];
 #pragma unroll
     for (int b = 0; b < BMAX; ++b) {
       if (on && b < B) {
-        if (blockIdx.x == 0 && resid_out) *reinterpret_cast<float4*>(resid_out + (size_t)b * K + 4 * col) = v[b];
+        if (emb != nullptr && blockIdx.x == 0) *reinterpret_cast<float4*>(S + (size_t)b * K + 4 * col) = v[b];
         *reinterpret_cast<float4*>(xs + b * K + 4 * col) = v[b];
       }
       ss[b] = fmaf(v[b].x, v[b].x, fmaf(v[b].y, v[b].y, fmaf(v[b].z, v[b].z, v[b].w * v[b].w)));
     }
-    // reduce-scatter over the warp: after the 5 steps lane b (< BMAX <= 16) holds the warp's sum for sequence b
-    float mine = 0.f;
+    reduce_scatter<BMAX>(ss, lane);
 #pragma unroll
-    for (int b = 0; b < BMAX; ++b) {
-      float t = ss[b];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-      if (lane == b) mine = t;
+    for (int j = 0; j < RsPlan<BMAX>::NF; ++j) {
+      const int i = rs_index<BMAX>(lane, j);
+      if (i < BMAX) ssq[(c * kDecWarps + warp) * BMAX + i] = ss[j];
     }
-    if (lane < BMAX) ssq[(c * kDecWarps + warp) * BMAX + lane] = mine;
   }
   __syncthreads();
 #pragma unroll
@@ -304,13 +378,6 @@ __device__ __forceinline__ void stage_norm(float* xs, float* ssq, const float* h
   }
 }
 
-// registers of the SSM phase that do not depend on x_proj: loaded before the barrier opens
-template <int BH>
-struct SsmPre {
-  float4 A4, w4, h[BH];
-  float dtb, Dd;
-};
-
 constexpr int kRW = 4;   // weight rows per task of the "rows" phases
 
 template <typename TW, int BMAX, bool BIG>
@@ -320,20 +387,25 @@ __global__ void __launch_bounds__(kDecThreads, 1) decode_token_kernel(const Mamb
   constexpr int NQ1 = BIG ? 4 : 1;              // "rows" phases: chunks along K, tiles in the ring
   constexpr int NB1 = BIG ? 2 : 1;
   constexpr int KH1 = K1 / 128 / NQ1;           // 16-byte pieces per lane, row and chunk
+  constexpr int NV1 = kRW * BMAX, NF1 = RsPlan<NV1>::NF;   // outputs per task / per lane after the reduce-scatter
   constexpr int SL4 = K2 / kDecWarps / 4;       // K-split phases: 16-byte pieces per warp slice (64 : 8)
   constexpr int KQ = SL4 < 16 ? SL4 : 16;       // active K-lanes
   constexpr int KV = SL4 / KQ;                  // 16-byte pieces per K-lane ...
   constexpr int KP = KV < 2 ? KV : 2;           // ... loaded KP at a time
   constexpr int NP = KV / KP;
   constexpr int RMAX4 = BIG ? 7 : 1;            // out_proj rows per CTA (x_proj: 2; both checked against gridDim by the host)
-  constexpr int BH = BMAX / 2;
-  constexpr int NI = 2;                         // SSM items (channel, batch parity) a half-warp preloads
-  constexpr int kMaxXD = 3 * 64;                // dt_rank + 2 * d_state
+  constexpr int DJ = BIG ? 14 : 2;              // SSM phase: channels per CTA (d = blockIdx + j*gridDim; checked by the host)
+  constexpr int NPAIR = DJ * BMAX;              // (channel, sequence) pairs per CTA
+  constexpr int NRND = (NPAIR + 15) / 16;       // state rows per half-warp
+  constexpr int XDP = 3 * 64 + 4;               // row stride of the x_proj outputs in shared memory (max XD, + 4: banks)
+  static_assert(NPAIR <= kDecThreads, "one thread per (channel, sequence) pair in the dt step");
   extern __shared__ __align__(16) float smem[];
   float* xs = smem;                             // [BMAX][K1] normalised activations of the "rows" phases
   float* red = xs + BMAX * K1;                  // [warps][8 rows][BMAX] partial sums of the K-split phases
-  float* xd_s = red + kDecWarps * 8 * BMAX;     // [B][XD] x_proj output of every sequence (SSM phase)
-  MambaDecodeLayer* Ls = reinterpret_cast<MambaDecodeLayer*>(xd_s + BMAX * kMaxXD);   // the layer descriptors
+  float* xd_s = red + kDecWarps * 8 * BMAX;     // [BMAX][XDP] x_proj output of every sequence (SSM phase)
+  float* A_s = xd_s + BMAX * XDP;               // [DJ][64] A rows of the CTA's channels
+  float* pr_s = A_s + DJ * 64;                  // [4][NPAIR]: delta*log2e, delta*u, D*u, silu(z) per pair
+  MambaDecodeLayer* Ls = reinterpret_cast<MambaDecodeLayer*>(pr_s + 4 * NPAIR);   // the layer descriptors
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int kq = lane & 15, bq = lane >> 4;
   const int nblk = gridDim.x;
@@ -351,10 +423,21 @@ __global__ void __launch_bounds__(kDecThreads, 1) decode_token_kernel(const Mamb
   };
   stamp(0);
   unsigned int target = 0;
-  // scratch carve-up (fp32): resid[2] | hidden | z | xc | x_dbl | y
-  auto resid = [&](int i) { return a.scratch + (size_t)(i & 1) * kMaxB * K1; };
-  float* const hidden = a.scratch + (size_t)2 * kMaxB * K1;
-  float* const zbuf = a.scratch + (size_t)3 * kMaxB * K1;
+  // MAMBA_DECODE_FLAG_BARRIER_STAMPS: every CTA records when it arrives at and when it leaves each grid barrier
+  unsigned long long* const bst = reinterpret_cast<unsigned long long*>(a.barrier + kStampWords) + (16 * a.n_layers + 8) +
+                                  (size_t)blockIdx.x * 2 * (4 * a.n_layers);
+  int nbar = 0;
+  auto bstamp = [&](int leave) {
+    if ((a.flags & MAMBA_DECODE_FLAG_BARRIER_STAMPS) && threadIdx.x == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+      bst[2 * nbar + leave] = t;
+    }
+    nbar += leave;
+  };
+  // scratch carve-up (fp32): S (residual stream) | z | xc | x_dbl | y
+  float* const S = a.scratch;
+  float* const zbuf = a.scratch + (size_t)kMaxB * K1;
   float* const xc = zbuf + (size_t)kMaxB * K2;
   float* const xdbl = xc + (size_t)kMaxB * K2;
   float* const ybuf = xdbl + (size_t)kMaxB * XD;
@@ -365,18 +448,19 @@ __global__ void __launch_bounds__(kDecThreads, 1) decode_token_kernel(const Mamb
 
   // ---- registers a warp loads ahead of the phase that uses them -------------------------------------------------------------
   WTile<kRW, KH1> t1[NB1];        // "rows" phases: the ring, holding the head of the warp's first task
-  float4 cst[kRW], cw[kRW];       // conv state / taps of the task's rows for sequence `lane`
-  float cb[kRW];
+  float4 cst[NF1], cw[NF1];       // conv state / taps of the (row, sequence) outputs this lane will hold
+  float cb[NF1];
   int l = 0;
   auto conv_pre = [&](int task) {
     const MambaDecodeLayer& L = Ls[l];
 #pragma unroll
-    for (int r = 0; r < kRW; ++r) {
-      const int n = task * kRW + r;
-      if (n < K2 && lane < B) {
-        cst[r] = *reinterpret_cast<const float4*>(L.conv_state + ((size_t)lane * K2 + n) * 4);
-        cw[r] = __ldg(reinterpret_cast<const float4*>(L.conv_weight + (size_t)n * 4));
-        cb[r] = L.conv_bias ? __ldg(L.conv_bias + n) : 0.f;
+    for (int j = 0; j < NF1; ++j) {
+      const int i = rs_index<NV1>(lane, j);
+      const int r = i / BMAX, b = i - r * BMAX, n = task * kRW + r;
+      if (i < NV1 && n < K2 && b < B) {
+        cst[j] = *reinterpret_cast<const float4*>(L.conv_state + ((size_t)b * K2 + n) * 4);
+        cw[j] = __ldg(reinterpret_cast<const float4*>(L.conv_weight + (size_t)n * 4));
+        cb[j] = L.conv_bias ? __ldg(L.conv_bias + n) : 0.f;
       }
     }
   };
@@ -399,15 +483,14 @@ __global__ void __launch_bounds__(kDecThreads, 1) decode_token_kernel(const Mamb
 
   for (; l < a.n_layers; ++l) {
     // ---- phase 1: norm + in_proj (+ conv step on the x half); "rows" mapping ----------------------------------------------
-    stage_norm<TW, K1, BMAX>(xs, red, hidden, resid(l + 1), resid(l), l == 0 ? static_cast<const TW*>(a.embedding) : nullptr, a.token,
-                             Ls[l].norm_weight, a.eps, B);
+    stage_norm<TW, K1, BMAX>(xs, red, S, l == 0 ? static_cast<const TW*>(a.embedding) : nullptr, a.token, Ls[l].norm_weight, a.eps, B);
     __syncthreads();
     stamp(10);
-    auto epi1 = [&](int r, int n, int b, float v) {
+    auto epi1 = [&](int j, int, int n, int b, float v) {
       if (n < K2) {  // conv branch: shift register + SiLU (simple_mamba.pyc @L233-237 for one position)
-        const float4 s = cst[r], w = cw[r];
+        const float4 s = cst[j], w = cw[j];
         *reinterpret_cast<float4*>(Ls[l].conv_state + ((size_t)b * K2 + n) * 4) = make_float4(s.y, s.z, s.w, v);
-        const float acc = fmaf(w.w, v, fmaf(w.z, s.w, fmaf(w.y, s.z, fmaf(w.x, s.y, cb[r]))));
+        const float acc = fmaf(w.w, v, fmaf(w.z, s.w, fmaf(w.y, s.z, fmaf(w.x, s.y, cb[j]))));
         xc[(size_t)b * K2 + n] = silu_f(acc);
       } else {
         zbuf[(size_t)b * K2 + (n - K2)] = v;
@@ -416,119 +499,144 @@ __global__ void __launch_bounds__(kDecThreads, 1) decode_token_kernel(const Mamb
     rows_phase<TW, kRW, KH1, NQ1, NB1, BMAX>(t1, static_cast<const TW*>(Ls[l].in_proj_weight), static_cast<const TW*>(Ls[l].in_proj_bias),
                                              2 * K2, K1, B, xs, gw, nwt, lane, conv_pre, epi1, [&]() { stamp(11); });
     stamp(1);
+    bstamp(0);
     grid_arrive(a.barrier);
     target += nblk;
     // ---- phase 2: x_proj; K-split mapping ------------------------------------------------------------------------------------
     prefetch_rows_l2<TW, KQ>(static_cast<const TW*>(Ls[l].x_proj_weight), XD, K2, 2, warp, lane);
     prefetch_rows_l2<TW, KQ>(static_cast<const TW*>(Ls[l].out_proj_weight), K1, K2, RMAX4, warp, lane);
+    {  // what the SSM phase will load while ITS barrier opens: state rows, A and dt_proj rows of the CTA's channels
+      const MambaDecodeLayer& L = Ls[l];
+      const int nl = (N * 4 + 127) >> 7, rl = (R * 4 + 127) >> 7;   // 128-byte lines per row
+      for (int i = threadIdx.x; i < NPAIR * nl; i += kDecThreads) {
+        const int pi = i / nl, c = i - pi * nl, j = pi / BMAX, b = pi - j * BMAX, d = blockIdx.x + j * nblk;
+        if (d < K2 && b < B) prefetch_l2(reinterpret_cast<const char*>(L.ssm_state + ((size_t)b * K2 + d) * N) + c * 128);
+      }
+      for (int i = threadIdx.x; i < DJ * (nl + rl); i += kDecThreads) {
+        const int j = i / (nl + rl), c = i - j * (nl + rl), d = blockIdx.x + j * nblk;
+        if (d < K2)
+          prefetch_l2(c < nl ? reinterpret_cast<const char*>(L.A + (size_t)d * N) + c * 128
+                             : reinterpret_cast<const char*>(L.dt_weight + (size_t)d * R) + (c - nl) * 128);
+      }
+    }
     grid_wait(a.barrier, target);
+    bstamp(1);
     stamp(2);
-    ksplit_rows<TW, 2, KQ, KP, NP, BH, BMAX, 8>(static_cast<const TW*>(Ls[l].x_proj_weight), XD, K2, xc, B, red, warp, kq, bq);
+    ksplit_rows<TW, 2, KQ, KP, NP, BMAX / 2, BMAX, 8>(static_cast<const TW*>(Ls[l].x_proj_weight), XD, K2, xc, B, red, warp, kq, bq);
     finish_rows<TW, BMAX, 8>(red, (const TW*)nullptr, XD, B, 2, [&](int n, int b, float v) { xdbl[(size_t)b * XD + n] = v; });
     stamp(3);
+    bstamp(0);
     grid_arrive(a.barrier);
     target += nblk;
-    // ---- phase 3: dt_proj + softplus + SSM step + D skip + gate; a half-warp per (channel, batch parity) ---------------------
+    // ---- phase 3: dt_proj + softplus, then SSM step + D skip + gate --------------------------------------------------------------
+    // The CTA owns channels d = blockIdx + j*gridDim.  Step A: one thread per (channel, sequence) pair forms
+    // delta = softplus(<dt_proj row, x_dbl[:R]> + bias) once (not once per lane of a reduction).  Step B: 16 lanes per
+    // pair, 4 states each; a half-warp walks pairs hp, hp + 16, ... whose state rows it loaded before the barrier opened.
     {
       const MambaDecodeLayer& L = Ls[l];
-      const int hl = lane & 15;
-      const unsigned mask = 0xffffu << (lane & 16);
-      const int hw0 = (threadIdx.x >> 4) * nblk + blockIdx.x, nhw = nblk * (kDecThreads >> 4);
-      const bool nact = hl < (N >> 2), ract = hl < (R >> 2);
-      const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      SsmPre<BH> sp[NI];
-      auto ssm_pre = [&](SsmPre<BH>& s, int item) {
-        const int d = item >> 1, p = item & 1;
-        s.A4 = nact ? __ldg(reinterpret_cast<const float4*>(L.A + (size_t)d * N) + hl) : z4;
-        s.w4 = ract ? __ldg(reinterpret_cast<const float4*>(L.dt_weight + (size_t)d * R) + hl) : z4;
-        s.dtb = L.dt_bias ? __ldg(L.dt_bias + d) : 0.f;
-        s.Dd = L.D ? __ldg(L.D + d) : 0.f;
+      const int hl = lane & 15, hp = threadIdx.x >> 4;
+      const bool nact = hl < (N >> 2);
+      float4 h[NRND];
 #pragma unroll
-        for (int i = 0; i < BH; ++i) {
-          const int b = min(p + 2 * i, B - 1);   // (padded sequences repeat the last one; nothing of theirs is stored)
-          s.h[i] = nact ? *(reinterpret_cast<const float4*>(L.ssm_state + ((size_t)b * K2 + d) * N) + hl) : z4;
-        }
-      };
-      // before the barrier opens: the items' state rows, A and dt_proj rows on their way into L2
-#pragma unroll
-      for (int k = 0; k < NI; ++k) {
-        const int item = hw0 + k * nhw;
-        if (item < 2 * K2) {
-          const int d = item >> 1, b = (item & 1) + 2 * hl;
-          const int nb = (N * 4 + 127) >> 7;   // 128-byte lines per row
-          if (b < B)
-            for (int c = 0; c < nb; ++c) prefetch_l2(reinterpret_cast<const char*>(L.ssm_state + ((size_t)b * K2 + d) * N) + c * 128);
-          if (hl == 15) prefetch_l2(L.A + (size_t)d * N), prefetch_l2(L.dt_weight + (size_t)d * R);
-          if (hl == 14 && N * 4 > 128) prefetch_l2(L.A + (size_t)d * N + 32);
-          if (hl == 13 && R * 4 > 128) prefetch_l2(L.dt_weight + (size_t)d * R + 32);
-        }
+      for (int k = 0; k < NRND; ++k) {
+        const int pi = hp + 16 * k, j = pi / BMAX, b = pi - j * BMAX, d = blockIdx.x + j * nblk;
+        h[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (pi < NPAIR && d < K2 && b < B && nact) h[k] = *(reinterpret_cast<const float4*>(L.ssm_state + ((size_t)b * K2 + d) * N) + hl);
       }
-      if (l + 1 < a.n_layers)
+      // A rows of the CTA's channels: one 16-byte piece per thread, requested now, parked in shared memory after the barrier
+      static_assert(DJ * 16 <= kDecThreads, "one A piece per thread");
+      float4 a_pre = make_float4(0.f, 0.f, 0.f, 0.f);
+      {
+        const int j = threadIdx.x >> 4, d = blockIdx.x + j * nblk;
+        if (j < DJ && d < K2 && nact) a_pre = __ldg(reinterpret_cast<const float4*>(L.A + (size_t)d * N) + hl);
+      }
+      if (l + 1 < a.n_layers) {
         prefetch_first(static_cast<const TW*>(Ls[l + 1].in_proj_weight), 2 * K2);
-      else
+        const int n0 = gw * kRW;   // conv state of the task's rows: kRW x 16 bytes per sequence
+        if (n0 < K2 && lane < B) prefetch_l2(Ls[l + 1].conv_state + ((size_t)lane * K2 + n0) * 4);
+        if (n0 < K2 && lane == 31) prefetch_l2(Ls[l + 1].conv_weight + (size_t)n0 * 4);
+      } else {
         prefetch_first(static_cast<const TW*>(a.head_weight), a.vocab);
+      }
       grid_wait(a.barrier, target);
+    bstamp(1);
       stamp(4);
-      // x_proj's output of every sequence -> shared memory (one L2 round trip for the CTA); the first item's state rows
-      // and gate inputs -> registers
-      for (int i = threadIdx.x; i < (B * XD) >> 2; i += kDecThreads) reinterpret_cast<float4*>(xd_s)[i] = ldcg4(xdbl + 4 * i);
-      float xcv[NI][BH], zv[NI][BH];
-      auto gate_pre = [&](float (&xv)[BH], float (&zz)[BH], int item) {
-#pragma unroll
-        for (int i = 0; i < BH; ++i) {
-          const int b = min((item & 1) + 2 * i, B - 1);
-          xv[i] = ldcg(xc + (size_t)b * K2 + (item >> 1)), zz[i] = ldcg(zbuf + (size_t)b * K2 + (item >> 1));
-        }
-      };
-      if (hw0 < 2 * K2) ssm_pre(sp[0], hw0), gate_pre(xcv[0], zv[0], hw0);
+      // x_proj's output of every sequence -> shared memory (one L2 round trip for the CTA)
+      for (int i = threadIdx.x; i < B * (XD >> 2); i += kDecThreads) {
+        const int b = i / (XD >> 2), c = i - b * (XD >> 2);
+        *reinterpret_cast<float4*>(xd_s + b * XDP + 4 * c) = ldcg4(xdbl + (size_t)b * XD + 4 * c);
+      }
+      // step A operands that do not need the staged rows
+      const int pj = threadIdx.x / BMAX, pb = threadIdx.x - pj * BMAX, pd = blockIdx.x + pj * nblk;
+      const bool pon = threadIdx.x < NPAIR && pd < K2 && pb < B;
+      float xcv = 0.f, zv = 0.f, dtb = 0.f, Dd = 0.f;
+      if (pon) {
+        xcv = ldcg(xc + (size_t)pb * K2 + pd), zv = ldcg(zbuf + (size_t)pb * K2 + pd);
+        dtb = L.dt_bias ? __ldg(L.dt_bias + pd) : 0.f, Dd = L.D ? __ldg(L.D + pd) : 0.f;
+      }
+      if ((threadIdx.x >> 4) < DJ) *reinterpret_cast<float4*>(A_s + (threadIdx.x >> 4) * 64 + 4 * hl) = a_pre;
       __syncthreads();
       stamp(12);
-      // one item: BH independent sequences, no branches inside (the chains of the sequences interleave)
-      auto ssm_item = [&](const SsmPre<BH>& s, const float (&xv)[BH], const float (&zz)[BH], int item) {
-        const int d = item >> 1, p = item & 1;
+      if (pon) {
+        const float4* wr = reinterpret_cast<const float4*>(L.dt_weight + (size_t)pd * R);
+        const float4* xr = reinterpret_cast<const float4*>(xd_s + pb * XDP);
+        float4 wdt[16];   // the pair's dt_proj row (R <= 64), all loads in flight at once
 #pragma unroll
-        for (int i = 0; i < BH; ++i) {
-          const int b = p + 2 * i, bc = min(b, B - 1);
-          const float* xd = xd_s + bc * XD;
-          const float4 xdt = ract ? *reinterpret_cast<const float4*>(xd + 4 * hl) : z4;
-          const float4 bb = nact ? *reinterpret_cast<const float4*>(xd + R + 4 * hl) : z4;
-          const float4 cc = nact ? *reinterpret_cast<const float4*>(xd + R + N + 4 * hl) : z4;
-          float dot = fmaf(s.w4.x, xdt.x, fmaf(s.w4.y, xdt.y, fmaf(s.w4.z, xdt.z, s.w4.w * xdt.w)));
+        for (int r4 = 0; r4 < 16; ++r4) wdt[r4] = r4 < (R >> 2) ? __ldg(wr + r4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
 #pragma unroll
-          for (int o = 8; o > 0; o >>= 1) dot += __shfl_xor_sync(mask, dot, o);
-          const float delta = softplus_fast(dot + s.dtb);
-          const float du = delta * xv[i], dl2 = delta * kLog2e;
-          float4 h4 = s.h[i];
-          h4.x = fmaf(ex2_approx(dl2 * s.A4.x), h4.x, du * bb.x);
-          h4.y = fmaf(ex2_approx(dl2 * s.A4.y), h4.y, du * bb.y);
-          h4.z = fmaf(ex2_approx(dl2 * s.A4.z), h4.z, du * bb.z);
-          h4.w = fmaf(ex2_approx(dl2 * s.A4.w), h4.w, du * bb.w);
-          if (nact && b < B) *(reinterpret_cast<float4*>(L.ssm_state + ((size_t)b * K2 + d) * N) + hl) = h4;
-          float y = fmaf(h4.x, cc.x, fmaf(h4.y, cc.y, fmaf(h4.z, cc.z, h4.w * cc.w)));
-#pragma unroll
-          for (int o = 8; o > 0; o >>= 1) y += __shfl_xor_sync(mask, y, o);
-          if (hl == 0 && b < B) ybuf[(size_t)b * K2 + d] = fmaf(s.Dd, xv[i], y) * silu_fast(zz[i]);
+        for (int r4 = 0; r4 < 16; ++r4) {
+          if (r4 < (R >> 2)) {
+            const float4 w = wdt[r4], x = xr[r4];
+            d0 = fmaf(w.x, x.x, d0), d1 = fmaf(w.y, x.y, d1), d2 = fmaf(w.z, x.z, d2), d3 = fmaf(w.w, x.w, d3);
+          }
         }
-      };
-      static_assert(NI == 2, "two register sets: the next item loads while this one is computed");
-      for (int item = hw0; item < 2 * K2; item += 2 * nhw) {
-        const int nxt = item + nhw;
-        if (item != hw0) ssm_pre(sp[0], item), gate_pre(xcv[0], zv[0], item);
-        if (nxt < 2 * K2) ssm_pre(sp[1], nxt), gate_pre(xcv[1], zv[1], nxt);
-        ssm_item(sp[0], xcv[0], zv[0], item);
-        if (nxt < 2 * K2) ssm_item(sp[1], xcv[1], zv[1], nxt);
+        const float delta = softplus_fast((d0 + d1) + (d2 + d3) + dtb);
+        pr_s[threadIdx.x] = delta * kLog2e;
+        pr_s[NPAIR + threadIdx.x] = delta * xcv;
+        pr_s[2 * NPAIR + threadIdx.x] = Dd * xcv;
+        pr_s[3 * NPAIR + threadIdx.x] = silu_fast(zv);
+      }
+      __syncthreads();
+      stamp(13);
+      const unsigned mask = 0xffffu << (lane & 16);
+#pragma unroll
+      for (int k = 0; k < NRND; ++k) {
+        const int pi = hp + 16 * k, j = pi / BMAX, b = pi - j * BMAX, d = blockIdx.x + j * nblk;
+        const bool on = pi < NPAIR && d < K2 && b < B;     // (uniform over the half-warp)
+        const int pc = on ? pi : 0, bc = on ? b : 0, jc = on ? j : 0;
+        const float dl2 = pr_s[pc], du = pr_s[NPAIR + pc];
+        const float4 A4 = *reinterpret_cast<const float4*>(A_s + jc * 64 + 4 * hl);
+        const float4 bb = *reinterpret_cast<const float4*>(xd_s + bc * XDP + R + (nact ? 4 * hl : 0));
+        const float4 cc = *reinterpret_cast<const float4*>(xd_s + bc * XDP + R + N + (nact ? 4 * hl : 0));
+        float4 h4 = h[k];
+        h4.x = fmaf(ex2_approx(dl2 * A4.x), h4.x, du * bb.x);
+        h4.y = fmaf(ex2_approx(dl2 * A4.y), h4.y, du * bb.y);
+        h4.z = fmaf(ex2_approx(dl2 * A4.z), h4.z, du * bb.z);
+        h4.w = fmaf(ex2_approx(dl2 * A4.w), h4.w, du * bb.w);
+        if (on && nact) *(reinterpret_cast<float4*>(L.ssm_state + ((size_t)b * K2 + d) * N) + hl) = h4;
+        float y = nact ? fmaf(h4.x, cc.x, fmaf(h4.y, cc.y, fmaf(h4.z, cc.z, h4.w * cc.w))) : 0.f;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) y += __shfl_xor_sync(mask, y, o);
+        if (on && hl == 0) ybuf[(size_t)b * K2 + d] = (y + pr_s[2 * NPAIR + pc]) * pr_s[3 * NPAIR + pc];
       }
     }
     stamp(5);
+    bstamp(0);
     grid_arrive(a.barrier);
     target += nblk;
-    // ---- phase 4: out_proj; K-split mapping ------------------------------------------------------------------------------------
+    // ---- phase 4: out_proj, added into the residual stream; K-split mapping -------------------------------------------------------
     grid_wait(a.barrier, target);
+    bstamp(1);
     stamp(6);
-    ksplit_rows<TW, RMAX4, KQ, KP, NP, BH, BMAX, 8>(static_cast<const TW*>(Ls[l].out_proj_weight), K1, K2, ybuf, B, red, warp, kq, bq);
+    ksplit_rows<TW, RMAX4, KQ, KP, NP, BMAX / 2, BMAX, 8>(static_cast<const TW*>(Ls[l].out_proj_weight), K1, K2, ybuf, B, red, warp, kq, bq);
     stamp(14);
-    finish_rows<TW, BMAX, 8>(red, static_cast<const TW*>(Ls[l].out_proj_bias), K1, B, RMAX4, [&](int n, int b, float v) { hidden[(size_t)b * K1 + n] = v; });
+    finish_rows<TW, BMAX, 8>(red, static_cast<const TW*>(Ls[l].out_proj_bias), K1, B, RMAX4, [&](int n, int b, float v) {
+      float* sp = S + (size_t)b * K1 + n;   // hidden + residual: this thread is the only one that touches the element
+      *sp = v + ldcg(sp);
+    });
     stamp(7);
+    bstamp(0);
     grid_arrive(a.barrier);
     target += nblk;
     if (l + 1 < a.n_layers) {
@@ -540,13 +648,15 @@ __global__ void __launch_bounds__(kDecThreads, 1) decode_token_kernel(const Mamb
       load_first(static_cast<const TW*>(a.head_weight), a.vocab);
     }
     grid_wait(a.barrier, target);
+    bstamp(1);
     stamp(8);
   }
   // ---- final norm + LM head; "rows" mapping ------------------------------------------------------------------------------------
-  stage_norm<TW, K1, BMAX>(xs, red, hidden, resid(a.n_layers + 1), nullptr, (const TW*)nullptr, a.token, a.norm_f_weight, a.eps, B);
+  stage_norm<TW, K1, BMAX>(xs, red, S, (const TW*)nullptr, a.token, a.norm_f_weight, a.eps, B);
   __syncthreads();
   rows_phase<TW, kRW, KH1, NQ1, NB1, BMAX>(t1, static_cast<const TW*>(a.head_weight), static_cast<const TW*>(a.head_bias), a.vocab, K1, B,
-                                           xs, gw, nwt, lane, [](int) {}, [&](int, int n, int b, float v) { a.logits[(size_t)b * a.logits_bs + n] = v; }, []() {});
+                                           xs, gw, nwt, lane, [](int) {}, [&](int, int, int n, int b, float v) { a.logits[(size_t)b * a.logits_bs + n] = v; },
+                                           []() {});
   stamp(9);
 }
 
@@ -592,7 +702,7 @@ extern "C" size_t mamba_decode_token_scratch_bytes(int d_model, int d_inner, int
 
 extern "C" size_t mamba_decode_token_barrier_bytes(int n_layers) {
   if (n_layers <= 0) return 0;
-  return sizeof(unsigned int) * mb::kStampWords + sizeof(unsigned long long) * (size_t)(16 * n_layers + 8);
+  return sizeof(unsigned int) * mb::kStampWords + sizeof(unsigned long long) * ((size_t)(16 * n_layers + 8) + (size_t)256 * 2 * 4 * n_layers);
 }
 
 extern "C" int mamba_decode_token(const MambaDecodeTokenArgs* a, void* stream) {
@@ -616,10 +726,12 @@ extern "C" int mamba_decode_token(const MambaDecodeTokenArgs* a, void* stream) {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
   // rows per CTA of the K-split phases are compile-time: x_proj <= 2, out_proj <= 7 (1)
-  if (a->dt_rank + 2 * a->d_state > 2 * nsm || a->d_model > (big ? 7 : 1) * nsm)
+  if (a->dt_rank + 2 * a->d_state > 2 * nsm || a->d_model > (big ? 7 : 1) * nsm || a->d_inner > (big ? 14 : 2) * nsm)
     return set_error(MAMBA_ESIZE, "decode_token: %d SMs are too few for this shape", nsm);
   const int bmax = (a->batch + 1) & ~1;
-  const size_t smem = sizeof(float) * ((size_t)bmax * a->d_model + (size_t)kDecWarps * 8 * bmax + (size_t)bmax * 192) +
+  const int dj = big ? 14 : 2;
+  const size_t smem = sizeof(float) * ((size_t)bmax * a->d_model + (size_t)kDecWarps * 8 * bmax + (size_t)bmax * 196 + (size_t)dj * 64 +
+                                       (size_t)4 * dj * bmax) +
                       sizeof(MambaDecodeLayer) * (size_t)a->n_layers;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(nsm), cfg.blockDim = dim3(kDecThreads), cfg.dynamicSmemBytes = smem;

@@ -322,6 +322,7 @@ int mamba_sample_step(const MambaSampleStepArgs* args, void* stream);
  * Supported shapes: (d_model, d_inner) = (1024, 2048) or (128, 256); d_state, dt_rank multiples of 4 up to 64; d_conv 4.
  * ------------------------------------------------------------------------------------------ */
 #define MAMBA_DECODE_FLAG_STAMPS 1
+#define MAMBA_DECODE_FLAG_BARRIER_STAMPS 2 /* every CTA c: uint64 ns [4*n_layers][arrive, leave] after the event stamps */
 typedef struct MambaDecodeLayer {
   const float* norm_weight;       /* [d_model] RMSNorm of the residual block                 */
   const void* in_proj_weight;     /* [2*d_inner, d_model]  (w_dtype)                         */

@@ -11,7 +11,7 @@ nseq = int(sys.argv[1]) if len(sys.argv) > 1 else 10
 model = train.new_model("mamba").to(dev).eval()
 src, _, meta = synthetic.batch(nseq, 256, seed=3)
 NAMES = {1: "P1 end", 2: "bar", 3: "P2 end", 4: "bar", 5: "P3 end", 6: "bar", 7: "P4 end", 8: "bar", 9: "head end",
-         10: "P1 staged", 11: "P1 mul done", 12: "P3 staged", 14: "P4 mul done"}
+         10: "P1 staged", 11: "P1 mul done", 12: "P3 staged", 13: "P3 dt done", 14: "P4 mul done"}
 with torch.no_grad():
     dec = generate.RecurrentDecoder(model, nseq, use_graph=False, max_new_tokens=64)
     dec.prefill(src.to(dev), meta.to(dev))
