@@ -342,7 +342,7 @@ def decode_leg(dev, rank, world, barrier, n_new=2000, n_seq=10, prompt=2048):
     torch.manual_seed(0)
     model = train.new_model("mamba").to(dev).eval()
     src, _, meta = synthetic.batch(n_seq, prompt, seed=3)
-    ms = 0.0
+    ms, dec = 0.0, None
     if hi > lo:
         with torch.no_grad():
             dec = generate.RecurrentDecoder(model, hi - lo, use_graph=True, max_new_tokens=n_new + 16)
@@ -369,7 +369,9 @@ def decode_leg(dev, rank, world, barrier, n_new=2000, n_seq=10, prompt=2048):
     return {"sequences": n_seq, "sequences_per_rank_max": -(-n_seq // world), "prompt": prompt, "new_tokens_per_seq": n_new,
             "timed_steps": n, "dtype": "f32", "ms_per_step": ms / n, "tokens_per_sec": n_seq * n / (ms * 1e-3),
             "sharding": f"{n_seq} sequences over {world} rank(s), no collective",
-            "mode": "recurrent decode: 4 launches per layer + head + on-device sampler, one CUDA graph per token, greedy"}
+            "mode": ("one persistent cooperative kernel per token (csrc/decode.cu: all layers + head, grid barrier between phases) + "
+                     "the on-device sampler, one CUDA graph per token, greedy" if getattr(dec, "plan", None) is not None else
+                     "recurrent decode: 4 launches per layer + head + on-device sampler, one CUDA graph per token, greedy")}
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -532,9 +534,18 @@ def main():
         # shape (only valid for the bf16 default workload it was taken on)
         traffic, traffic_src = None, None
         if args.dtype == "bf16":
-            for tag in ("r02", "r01"):   # newest capture of this kernel at this shape (the kernel's source hash is in the file)
+            import hashlib
+            csrc = ROOT / "deep-learning-based-sequence-models-for-music-generation_b200" / "csrc"
+            for tag in ("r02", "r01"):   # newest capture of this kernel at this shape
                 try:
                     rec = json.loads((ROOT / "profiles" / f"{tag}_ncu_traffic.json").read_text())[dom]
+                    if "source_sha" in rec:   # stale capture (the kernel's sources changed since): report null, not an old number
+                        h = hashlib.sha256()
+                        for f in rec["source_files"]:
+                            h.update((csrc / f).read_bytes())
+                        if h.hexdigest()[:16] != rec["source_sha"]:
+                            traffic_src = f"profiles/{tag}_ncu_traffic.json is stale (kernel sources changed since the capture)"
+                            break
                     traffic, traffic_src = rec["traffic_bytes"], f"profiles/{tag}_ncu_traffic.json ({rec.get('capture', 'ncu --set full')})"
                     break
                 except Exception:

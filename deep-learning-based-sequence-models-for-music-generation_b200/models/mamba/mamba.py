@@ -26,6 +26,7 @@ from __future__ import annotations
 
 import contextlib
 import math
+import os
 import warnings
 from dataclasses import dataclass
 from types import SimpleNamespace
@@ -40,6 +41,24 @@ from ...configs import common as cc
 from ...configs import mamba as cm
 
 __all__ = ["ModelArgs", "Mamba", "ResidualBlock", "MambaBlock", "RMSNorm"]
+
+
+class _Nvtx:
+    """NVTX ranges per layer and phase (tracing), opt-in with MAMBA_B200_NVTX=1: off by default
+    because a range is two python calls per phase and the step is launch-sensitive outside a CUDA graph.  Forward
+    ranges only (the backward's kernels carry their own names in nsys / ncu)."""
+    on = os.environ.get("MAMBA_B200_NVTX", "0") == "1"
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if _Nvtx.on:
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *exc):
+        if _Nvtx.on:
+            torch.cuda.nvtx.range_pop()
 
 
 @dataclass
@@ -251,15 +270,19 @@ class MambaBlock(nn.Module):  # simple_mamba @L184
         if torch.is_grad_enabled() and xz.requires_grad and xz.is_cuda and torch.is_autocast_enabled("cuda"):
             plan = ops.MixerGradPlan(xz.shape, xz.shape[:-1] + (p.dt_rank + 2 * p.d_state,))
         xs, res = ops.split_fn(xz, [p.d_inner, p.d_inner], plan, "xz")    # @L231  views, no copy
-        xc = ops.causal_conv1d_silu_fn(xs, self.conv1d.weight, self.conv1d.bias, plan=plan)   # @L233-237 (one kernel)
-        x_dbl = _linear(xc, self.x_proj.weight)                           # @L273
-        dt_r, Bm, Cm = ops.split_fn(x_dbl, [p.dt_rank, p.d_state, p.d_state], plan, "xdbl")  # @L275 views
-        dt_raw = _linear(dt_r, self.dt_proj.weight, plan=plan)            # @L276: bias + softplus fused below
+        with _Nvtx("conv1d_silu"):
+            xc = ops.causal_conv1d_silu_fn(xs, self.conv1d.weight, self.conv1d.bias, plan=plan)   # @L233-237 (one kernel)
+        with _Nvtx("x_proj_dt_proj"):
+            x_dbl = _linear(xc, self.x_proj.weight)                           # @L273
+            dt_r, Bm, Cm = ops.split_fn(x_dbl, [p.dt_rank, p.d_state, p.d_state], plan, "xdbl")  # @L275 views
+            dt_raw = _linear(dt_r, self.dt_proj.weight, plan=plan)            # @L276: bias + softplus fused below
         # A = -exp(A_log) (@L270) is formed inside the kernels; the gradient comes back w.r.t. A_log
-        y = ops.selective_scan_fn(xc, dt_raw, self.A_log, Bm, Cm, self.D.float(), z=res,
-                                  delta_bias=self.dt_proj.bias.float(), delta_softplus=True,
-                                  A_is_log=True, plan=plan)               # @L270, @L276-278, @L241
-        return _linear(y, self.out_proj.weight, self.out_proj.bias)       # @L243
+        with _Nvtx("selective_scan"):
+            y = ops.selective_scan_fn(xc, dt_raw, self.A_log, Bm, Cm, self.D.float(), z=res,
+                                      delta_bias=self.dt_proj.bias.float(), delta_softplus=True,
+                                      A_is_log=True, plan=plan)               # @L270, @L276-278, @L241
+        with _Nvtx("out_proj"):
+            return _linear(y, self.out_proj.weight, self.out_proj.bias)       # @L243
 
     # ---- inference: full-sequence forward that also leaves the recurrent state behind ---------------
     @torch.no_grad()
@@ -447,11 +470,14 @@ class Mamba(nn.Module):
         # Layout P, @L90-96.  `mixer(norm(x)) + x` per layer, with each `+ x` fused into the next RMSNorm:
         # the residual stream is read and written once per layer.
         resid, hidden = x, None
-        for layer in self.layers:
-            normed, resid = layer.norm(hidden, resid)
-            hidden = layer.mixer(normed)
-        normed, _ = self.norm_f(hidden, resid)
-        return self._head(normed[:, n_meta:])  # rows are independent: slicing before the GEMM == logits[:, 6:]
+        for i, layer in enumerate(self.layers):
+            with _Nvtx(f"layer{i}"):
+                with _Nvtx("rmsnorm_residual"):
+                    normed, resid = layer.norm(hidden, resid)
+                hidden = layer.mixer(normed)
+        with _Nvtx("norm_f_head"):
+            normed, _ = self.norm_f(hidden, resid)
+            return self._head(normed[:, n_meta:])  # rows are independent: slicing before the GEMM == logits[:, 6:]
 
     def _head(self, x):
         """lm_head (layout P) with the vocabulary padded to a multiple of 8 INSIDE the GEMM: 17914 columns make
