@@ -39,7 +39,7 @@ constexpr int kStampWords = 4;  // barrier words before the time stamps (MAMBA_D
 __device__ __forceinline__ float ldcg(const float* p) { return __ldcg(p); }
 __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 
-// ---- grid barrier: monotone arrival counter (the host zeroes it before every launch) -----------------------------------
+// ---- grid barrier: monotone arrival counter (zero at launch: the previous launch's last CTA resets it) -----------------------------------
 __device__ __forceinline__ void grid_arrive(unsigned int* bar) {
   __syncthreads();   // every write of this CTA happens-before thread 0's release
   if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(bar), "r"(1u) : "memory");
@@ -658,6 +658,14 @@ __global__ void __launch_bounds__(kDecThreads, 1) decode_token_kernel(const Mamb
                                            xs, gw, nwt, lane, [](int) {}, [&](int, int, int n, int b, float v) { a.logits[(size_t)b * a.logits_bs + n] = v; },
                                            []() {});
   stamp(9);
+  // the last CTA to finish zeroes the barrier words for the next launch (no CTA reads them after the final barrier)
+  if (threadIdx.x == 0) {
+    const unsigned int done = atomicAdd(a.barrier + 1, 1u);
+    if (done == (unsigned int)nblk - 1u) {
+      a.barrier[0] = 0u;
+      a.barrier[1] = 0u;
+    }
+  }
 }
 
 template <typename TW, int BMAX, bool BIG>
@@ -740,8 +748,6 @@ extern "C" int mamba_decode_token(const MambaDecodeTokenArgs* a, void* stream) {
   attr[0].id = cudaLaunchAttributeCooperative;   // every CTA resident at once: the grid barrier cannot deadlock
   attr[0].val.cooperative = 1;
   cfg.attrs = attr, cfg.numAttrs = 1;
-  cudaError_t e = cudaMemsetAsync(a->barrier, 0, sizeof(unsigned int), cfg.stream);   // the arrival counter
-  if (e != cudaSuccess) return set_error(MAMBA_ELAUNCH, "decode_token: memset: %s", cudaGetErrorString(e));
   int rc;
   if (a->w_dtype == MAMBA_F32)
     rc = big ? launch_decode_b<float, true>(*a, cfg, bmax) : launch_decode_b<float, false>(*a, cfg, bmax);

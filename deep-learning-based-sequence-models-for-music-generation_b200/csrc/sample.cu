@@ -47,26 +47,43 @@ __global__ void __launch_bounds__(kSampleThreads) sample_step_kernel(const Mamba
   const float* w = a.dist + (int64_t)bucket * V;
 
   Cand c0{-INFINITY, 0x7fffffff}, c1 = c0, c2 = c0;  // this thread's three best, in order
-  for (int v = tid; v < V; v += kSampleThreads) {
-    const float x = lg[v], l0 = lse[v];
-    // logaddexp as torch computes it: max + log1p(exp(-|d|))
-    const float m = fmaxf(x, l0);
-    const float l1 = (x == l0 && isinf(x)) ? x : m + log1pf(expf(-fabsf(x - l0)));
-    lse[v] = l1;
-    float f = -(x - l1) * w[v];
-    const int c = counts[v];
-    if (c > 0) {
-      const int cls = (v >= a.class_bounds[0]) + (v >= a.class_bounds[1]) + (v >= a.class_bounds[2]) + (v >= a.class_bounds[3]);
-      const int rule = a.pen_rule[cls];
-      float pen = 1.f;
-      if (rule == 1) pen = a.pen_table[cls * 128 + min(c, 127)];                           // python: min(base ** count, cap)
-      else if (rule == 2) pen = c >= 10 ? (float)(1.1 * (double)c) : 1.f;                  // generate_midi_many.py:33-35
-      f = f / pen;
+  // kU vocabulary entries per thread and round: their 4 x kU loads are all issued before the first use (the rows are
+  // cold — the decode kernel has just streamed 450 MB through L2 — so a round is one DRAM round trip, not kU of them)
+  constexpr int kU = 6;
+#pragma unroll 1
+  for (int v0 = tid; v0 < V; v0 += kSampleThreads * kU) {
+    float xs[kU], ls[kU], ws[kU];
+    int cs[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int v = v0 + u * kSampleThreads;
+      const bool ok = v < V;
+      xs[u] = ok ? lg[v] : 0.f, ls[u] = ok ? lse[v] : 0.f, ws[u] = ok ? w[v] : 0.f, cs[u] = ok ? counts[v] : 0;
     }
-    const Cand x3{f, v};
-    if (better(x3, c0)) c2 = c1, c1 = c0, c0 = x3;
-    else if (better(x3, c1)) c2 = c1, c1 = x3;
-    else if (better(x3, c2)) c2 = x3;
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int v = v0 + u * kSampleThreads;
+      if (v >= V) break;
+      const float x = xs[u], l0 = ls[u];
+      // logaddexp as torch computes it: max + log1p(exp(-|d|))
+      const float m = fmaxf(x, l0);
+      const float l1 = (x == l0 && isinf(x)) ? x : m + log1pf(expf(-fabsf(x - l0)));
+      lse[v] = l1;
+      float f = -(x - l1) * ws[u];
+      const int c = cs[u];
+      if (c > 0) {
+        const int cls = (v >= a.class_bounds[0]) + (v >= a.class_bounds[1]) + (v >= a.class_bounds[2]) + (v >= a.class_bounds[3]);
+        const int rule = a.pen_rule[cls];
+        float pen = 1.f;
+        if (rule == 1) pen = a.pen_table[cls * 128 + min(c, 127)];                           // python: min(base ** count, cap)
+        else if (rule == 2) pen = c >= 10 ? (float)(1.1 * (double)c) : 1.f;                  // generate_midi_many.py:33-35
+        f = f / pen;
+      }
+      const Cand x3{f, v};
+      if (better(x3, c0)) c2 = c1, c1 = c0, c0 = x3;
+      else if (better(x3, c1)) c2 = c1, c1 = x3;
+      else if (better(x3, c2)) c2 = x3;
+    }
   }
   // three rounds of block-wide argmax; the winner's thread moves its next candidate up
   const int rounds = a.mode == 0 ? 1 : 3;

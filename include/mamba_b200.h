@@ -314,8 +314,9 @@ int mamba_sample_step(const MambaSampleStepArgs* args, void* stream);
  * mamba_linear_step, mamba_ssm_step) become one cooperative grid (one CTA per SM) with a grid barrier between phases.
  * `layers` is a DEVICE array of n_layers descriptors; `token` [B] int64 is read on the device (it is the sampler's
  * output of the previous step); `logits` [B, vocab] fp32 feeds mamba_sample_step.  conv_state / ssm_state are updated
- * in place.  `scratch` (mamba_decode_token_scratch_bytes) and `barrier` (mamba_decode_token_barrier_bytes: the arrival
- * counter of the grid barrier, which the call zeroes, followed by room for time stamps) are caller-owned.
+ * in place.  `scratch` (mamba_decode_token_scratch_bytes) and `barrier` (mamba_decode_token_barrier_bytes: the two
+ * counters of the grid barrier followed by room for time stamps) are caller-owned; the caller zeroes the first 16 bytes
+ * of `barrier` once (and again after a failed launch), every completed call leaves them zero.
  * With MAMBA_DECODE_FLAG_STAMPS thread 0 of CTA 0 appends (event id << 56 | %globaltimer ns) as uint64 from byte 16 of
  * `barrier`: id 0 at kernel start; per layer 1..8 (end of phase / barrier open, for the 4 phases) and 10..14 inside the
  * phases; 9 at the end of the head (at most 16*n_layers + 8 values).
@@ -355,7 +356,7 @@ typedef struct MambaDecodeTokenArgs {
   const void* head_bias;          /* [vocab] or NULL                                          */
   float* logits;  int64_t logits_bs;  /* [B, vocab] fp32                                      */
   float* scratch; size_t scratch_bytes;
-  unsigned int* barrier;          /* mamba_decode_token_barrier_bytes(n_layers), any contents */
+  unsigned int* barrier;          /* mamba_decode_token_barrier_bytes(n_layers); first 16 bytes zero */
 } MambaDecodeTokenArgs;
 
 size_t mamba_decode_token_scratch_bytes(int d_model, int d_inner, int d_state, int dt_rank);
