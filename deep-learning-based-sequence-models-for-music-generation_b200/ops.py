@@ -277,8 +277,10 @@ def selective_scan_fn(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_
     z: [B, L, D].  Returns out [B, L, D] = (scan(u, delta, A, B, C) + D*u) * silu(z).
     A_is_log: `A` is the A_log parameter; the kernels form A = -exp(A_log) (simple_mamba @L270) themselves and the
     gradient comes back w.r.t. A_log (saves five elementwise launches per layer and step)."""
-    return SelectiveScanFn.apply(u, delta, A, B, C, D, z, delta_bias, bool(delta_softplus),
-                                 SCAN_CHUNK if chunk is None else int(chunk), bool(A_is_log), plan)
+    chunk = SCAN_CHUNK if chunk is None else int(chunk)
+    if A.shape[1] > 64:
+        chunk = min(chunk, 8)   # the backward's shared-memory tiles for d_state > 64 only fit 8-step chunks (csrc/scan_bwd.cu)
+    return SelectiveScanFn.apply(u, delta, A, B, C, D, z, delta_bias, bool(delta_softplus), chunk, bool(A_is_log), plan)
 
 
 def selective_scan_prefill(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus=False, h_init=None):
