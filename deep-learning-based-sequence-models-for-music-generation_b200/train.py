@@ -295,14 +295,16 @@ class Trainer:
             layers = list(model.layers)
             per = -(-len(layers) // stages)
             self._stage_groups = [layers[i:i + per] for i in range(0, len(layers), per)]
-            # parameters of stage i; everything outside the layer stack that receives its last gradient contribution
-            # at the very end of the backward (embeddings, the tied head) joins stage 0, the final norm joins the
-            # last stage (its gradient is the first one to exist)
+            # parameters of stage i.  The final norm joins the last stage (its gradient is the first one to exist).
+            # Everything else outside the layer stack (embeddings, the tied head) receives its last gradient
+            # contribution at the very end of the backward and forms a stage of its own, AFTER stage 0: the bottom
+            # layers' bucket is then exchanged under the embedding backward instead of waiting for it, and what stays
+            # exposed at the end of the step is the exchange + update of the embedding matrix alone.
             groups = [[p for layer in g for p in layer.parameters()] for g in self._stage_groups]
             seen = {id(p) for g in groups for p in g}
             groups[-1] = groups[-1] + [p for p in model.norm_f.parameters() if id(p) not in seen]
             seen |= {id(p) for p in model.norm_f.parameters()}
-            groups[0] = groups[0] + [p for p in model.parameters() if id(p) not in seen]
+            groups.append([p for p in model.parameters() if id(p) not in seen])
             self._stage_params = [[p for p in g if p.requires_grad] for g in groups]
         # DDP broadcasts rank 0's parameters and buffers at construction (train_parallel.py:151); do the same, so that
         # ranks that seeded differently (or loaded different checkpoints) cannot apply averaged gradients to
@@ -432,7 +434,10 @@ class Trainer:
         m, groups = self.model, self._stage_groups
         cuts = []
         with torch.autocast(self.device.type, dtype=self.autocast_dtype, enabled=self.autocast_dtype is not None):
-            resid, hidden = m._embed(self.src, self.meta), None
+            emb = m._embed(self.src, self.meta)
+            # cut below the layer stack too: the embeddings (and the tied head) are the stage after stage 0
+            resid, hidden = (emb.detach().requires_grad_(True) if emb.requires_grad else emb), None
+            emb_in = resid
             for gi, group in enumerate(groups):
                 if gi > 0:  # cut the autograd graph below this group
                     rd, hd = resid.detach().requires_grad_(True), hidden.detach().requires_grad_(True)
@@ -453,6 +458,9 @@ class Trainer:
             with self._wgrad_scope():
                 torch.autograd.backward([r, h], [rd.grad, hd.grad])
             self._finish_stage(gi)
+        if emb_in is not emb:
+            torch.autograd.backward([emb], [emb_in.grad])
+        self._finish_stage(len(groups))
         if self._stage_optimizers is None:
             self.grads.finish()
             self.optimizer.step()

@@ -151,7 +151,7 @@ def _staged_worker(rank, world, port, q):
                                use_graph=False, stages=stages)
             assert (tr._stage_groups is None) == (stages == 1)
             if stages > 1:
-                assert len(tr.grads.buckets) == stages
+                assert len(tr.grads.buckets) == stages + 1   # the layer groups + the embedding / tied-head stage
                 assert all(p.grad is not None for p in model.parameters())
             losses = []
             for i in range(3):

@@ -374,7 +374,7 @@ def test_staged_backward_with_side_stream_adam_equals_plain_step(use_graph, stag
     try:
         ta = train.Trainer(a, lr=1e-3, batch_size=2, block_len=40, use_graph=use_graph, stages=1)
         tb = train.Trainer(b, lr=1e-3, batch_size=2, block_len=40, use_graph=use_graph, stages=stages)
-        assert ta._stage_groups is None and len(tb._stage_groups) == stages and len(tb._stage_optimizers) == stages
+        assert ta._stage_groups is None and len(tb._stage_groups) == stages and len(tb._stage_optimizers) == stages + 1
         for i in range(3):
             batch = [t.cuda() for t in synthetic.batch(2, 40, seed=40 + i)]
             la, lb = ta.step(*batch).item(), tb.step(*batch).item()
