@@ -9,18 +9,22 @@
 // them (4 per layer).  What bounds a phase is latency (DRAM round trip of the weights, L2 round trip of the
 // activations other SMs wrote, the barrier itself), so the kernel is organised around taking those off the critical
 // path:
-//   * the barrier is split into arrive (one release-RED per CTA) and wait (acquire-poll of the same counter); between
-//     the two every warp issues the loads of the NEXT phase that do not depend on this one — its weight rows, the
-//     SSM / conv states, A, dt_proj rows — into registers, so their DRAM latency overlaps the barrier;
-//   * phases with many rows per CTA (in_proj, head) give a warp two weight rows and the whole K axis (lanes stride K
-//     with 16-byte loads; activations in shared memory); K is cut in two register tiles so that the next task's
-//     loads are in flight while this task's second half is multiplied;
-//   * phases with few rows per CTA (x_proj: 192 rows, out_proj: 1024 rows over 148 CTAs) split K over the CTA's 16
-//     warps instead: a warp reads ITS 128-wide slice of the activations straight from L2 into registers (no staging
-//     of the full 80 KB row block, no __syncthreads before the math), lanes = 2 batch halves x 16 K-lanes, four
-//     shuffle steps per output, a fixed-order sum over the warps through 8 KB of shared memory;
-//   * the SSM phase maps a half-warp to (channel, batch parity): A and the dt_proj row are loaded once per channel, the
-//     <= 8 state rows of the half-warp are in registers before the barrier opens.
+//   * the barrier is split into arrive (one release-RED per CTA) and wait (acquire-poll of the same counter by thread
+//     0); between the two every warp issues what the NEXT phases need and does not depend on this one: L2 prefetches
+//     of weight rows (one or two phases ahead), of the SSM state rows, A and dt_proj rows, and register loads of the
+//     first weight tiles / conv state / state rows.  The polling thread must not have DRAM loads outstanding (its
+//     acquire waits for them): whatever is loaded into registers before the poll was prefetched into L2 a phase earlier;
+//   * phases with many rows per CTA (in_proj, head; "rows" mapping) give a warp four weight rows and the whole K axis
+//     (lanes stride K with 16-byte loads; activations normalised once into shared memory by all threads).  K is cut
+//     in four chunks through a ring of two register tiles, so that the next chunk — of this task or of the warp's next
+//     one — is in flight while this one is multiplied; packed fp32x2 accumulation; one warp reduce-scatter per task;
+//   * phases with few rows per CTA (x_proj: 192 rows, out_proj: 1024 rows over 148 CTAs; "K-split" mapping) split K
+//     over the CTA's 8 warps instead: a warp reads ITS slice of the activations straight from L2 into registers (no
+//     staging of the full 80 KB row block, no __syncthreads before the math), lanes = 2 batch halves x 16 K-lanes,
+//     reduce-scatter over the K-lanes, a fixed-order sum over the warps through shared memory.  out_proj's epilogue
+//     adds into the residual stream in place;
+//   * the SSM phase: one thread per (channel, sequence) forms delta = softplus(<dt_proj row, x_dbl> + bias) once, then 16
+//     lanes per state row (4 states each) do the update; the state rows are in registers before the barrier opens.
 // Activations between phases live in a small global scratch (read with ld.global.cg: they were written by other SMs in
 // the same launch); the residual stream is fp32; weights are fp32 or bf16; batch <= 16 (template BMAX = batch rounded
 // up to even; padded rows are zeros and their outputs are dropped).
