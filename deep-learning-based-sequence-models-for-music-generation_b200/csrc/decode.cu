@@ -326,6 +326,12 @@ __device__ __forceinline__ void stage_norm(float* xs, float* ssq, float* S, cons
   constexpr int C4 = K / 4;                                              // 16-byte pieces per row
   constexpr int NC = (C4 + kDecThreads - 1) / kDecThreads;              // ... per thread and row (1)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float4 g[NC];   // the norm weights of this thread's columns: requested first, used last
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const int col = threadIdx.x + c * kDecThreads;
+    g[c] = col < C4 ? __ldg(reinterpret_cast<const float4*>(norm_w) + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
     const int col = threadIdx.x + c * kDecThreads;
@@ -361,22 +367,24 @@ __device__ __forceinline__ void stage_norm(float* xs, float* ssq, float* S, cons
     }
   }
   __syncthreads();
+  // lane b of every warp sums sequence b's partials (fixed order) and forms rstd; the other lanes fetch it by shuffle
+  float rs = 0.f;
+  if (lane < BMAX) {
+    float tot = 0.f;
 #pragma unroll
-  for (int c = 0; c < NC; ++c) {
-    const int col = threadIdx.x + c * kDecThreads;
-    if (col < C4) {
-      const float4 g = __ldg(reinterpret_cast<const float4*>(norm_w) + col);
+    for (int w = 0; w < NC * kDecWarps; ++w) tot += ssq[w * BMAX + lane];
+    rs = rsqrtf(tot / (float)K + eps);
+  }
 #pragma unroll
-      for (int b = 0; b < BMAX; ++b) {
-        if (b < B) {
-          float tot = 0.f;
+  for (int b = 0; b < BMAX; ++b) {
+    const float rstd = __shfl_sync(0xffffffffu, rs, b);
 #pragma unroll
-          for (int w = 0; w < NC * kDecWarps; ++w) tot += ssq[w * BMAX + b];
-          const float rstd = rsqrtf(tot / (float)K + eps);
-          float4 v = *reinterpret_cast<float4*>(xs + b * K + 4 * col);
-          v = make_float4(v.x * rstd * g.x, v.y * rstd * g.y, v.z * rstd * g.z, v.w * rstd * g.w);
-          *reinterpret_cast<float4*>(xs + b * K + 4 * col) = v;
-        }
+    for (int c = 0; c < NC; ++c) {
+      const int col = threadIdx.x + c * kDecThreads;
+      if (col < C4 && b < B) {
+        float4 v = *reinterpret_cast<float4*>(xs + b * K + 4 * col);
+        v = make_float4(v.x * rstd * g[c].x, v.y * rstd * g[c].y, v.z * rstd * g[c].z, v.w * rstd * g[c].w);
+        *reinterpret_cast<float4*>(xs + b * K + 4 * col) = v;
       }
     }
   }
@@ -388,8 +396,8 @@ template <typename TW, int BMAX, bool BIG>
 __global__ void __launch_bounds__(kDecThreads, 1) decode_token_kernel(const MambaDecodeTokenArgs a) {
   constexpr int K1 = BIG ? 1024 : 128;          // d_model
   constexpr int K2 = BIG ? 2048 : 256;          // d_inner
-  constexpr int NQ1 = BIG ? 4 : 1;              // "rows" phases: chunks along K, tiles in the ring
-  constexpr int NB1 = BIG ? 2 : 1;
+  constexpr int NQ1 = BIG ? 8 : 1;              // "rows" phases: chunks along K, tiles in the ring (half of K in flight)
+  constexpr int NB1 = BIG ? 4 : 1;
   constexpr int KH1 = K1 / 128 / NQ1;           // 16-byte pieces per lane, row and chunk
   constexpr int NV1 = kRW * BMAX, NF1 = RsPlan<NV1>::NF;   // outputs per task / per lane after the reduce-scatter
   constexpr int SL4 = K2 / kDecWarps / 4;       // K-split phases: 16-byte pieces per warp slice (64 : 8)
@@ -522,6 +530,11 @@ __global__ void __launch_bounds__(kDecThreads, 1) decode_token_kernel(const Mamb
           prefetch_l2(c < nl ? reinterpret_cast<const char*>(L.A + (size_t)d * N) + c * 128
                              : reinterpret_cast<const char*>(L.dt_weight + (size_t)d * R) + (c - nl) * 128);
       }
+      if (threadIdx.x < 2 * DJ) {   // dt_proj bias and D of those channels
+        const int d = blockIdx.x + (threadIdx.x >> 1) * nblk;
+        const float* v = (threadIdx.x & 1) ? L.D : L.dt_bias;
+        if (d < K2 && v) prefetch_l2(v + d);
+      }
     }
     grid_wait(a.barrier, target);
     bstamp(1);
@@ -554,6 +567,10 @@ __global__ void __launch_bounds__(kDecThreads, 1) decode_token_kernel(const Mamb
         const int j = threadIdx.x >> 4, d = blockIdx.x + j * nblk;
         if (j < DJ && d < K2 && nact) a_pre = __ldg(reinterpret_cast<const float4*>(L.A + (size_t)d * N) + hl);
       }
+      {  // the next RMSNorm's weights (K1 floats)
+        const float* nw = l + 1 < a.n_layers ? Ls[l + 1].norm_weight : a.norm_f_weight;
+        if (threadIdx.x * 32 < K1) prefetch_l2(nw + threadIdx.x * 32);
+      }
       if (l + 1 < a.n_layers) {
         prefetch_first(static_cast<const TW*>(Ls[l + 1].in_proj_weight), 2 * K2);
         const int n0 = gw * kRW;   // conv state of the task's rows: kRW x 16 bytes per sequence
@@ -563,7 +580,7 @@ __global__ void __launch_bounds__(kDecThreads, 1) decode_token_kernel(const Mamb
         prefetch_first(static_cast<const TW*>(a.head_weight), a.vocab);
       }
       grid_wait(a.barrier, target);
-    bstamp(1);
+      bstamp(1);
       stamp(4);
       // x_proj's output of every sequence -> shared memory (one L2 round trip for the CTA)
       for (int i = threadIdx.x; i < B * (XD >> 2); i += kDecThreads) {
