@@ -152,3 +152,40 @@ def test_weight_shadows_are_used_only_while_the_parameter_is_unchanged():
     assert not WeightShadows.stale([w])
     assert torch.equal(WeightShadows.get(w, torch.bfloat16), w.detach().to(torch.bfloat16))
     WeightShadows.table.pop(id(w))
+
+
+def test_mamba2_oracle_recurrence_equals_the_published_dual_form():
+    """oracle/mamba2_ref.py cannot be pinned against mamba_ssm (absent).  What can be checked without it: the two
+    PUBLISHED forms of the Mamba-2 operator agree — the recurrence the oracle restates, and the state-space-dual
+    (masked-attention) form of the same paper, written here independently:
+        Y = (Lmask * (C B^T)) (dt * X) + D X,   Lmask[i, j] = exp(sum_{k=j+1..i} dt_k A) for i >= j, else 0."""
+    import torch.nn.functional as F
+    from oracle.mamba2_ref import Mamba2Ref
+    torch.manual_seed(3)
+    m = Mamba2Ref(d_model=32, d_state=16, d_conv=4, expand=2, headdim=8).double()
+    with torch.no_grad():
+        m.D.add_(0.3 * torch.randn_like(m.D))
+        m.norm.weight.add_(0.1 * torch.randn_like(m.norm.weight))
+    u = torch.randn(2, 19, 32, dtype=torch.double)
+    with torch.no_grad():
+        want = m(u)
+        # dual form, head by head
+        Bsz, L, _ = u.shape
+        H, P, N = m.nheads, m.headdim, m.d_state
+        z, xBC, dt = torch.split(m.in_proj(u), [m.d_inner, m.d_inner + 2 * N, H], dim=-1)
+        dt = F.softplus(dt + m.dt_bias)
+        xBC = F.silu(m.conv1d(xBC.transpose(1, 2))[..., :L].transpose(1, 2))
+        x, Bm, Cm = torch.split(xBC, [m.d_inner, N, N], dim=-1)
+        x = x.reshape(Bsz, L, H, P)
+        A = -torch.exp(m.A_log)
+        cum = torch.cumsum(dt * A, dim=1)                                        # [B, L, H]
+        seg = cum[:, :, None, :] - cum[:, None, :, :]                            # [B, i, j, H] = sum_{k=j+1..i}
+        mask = torch.tril(torch.ones(L, L, dtype=torch.bool))[None, :, :, None]
+        Lm = torch.where(mask, torch.exp(seg.masked_fill(~mask, 0.0)), torch.zeros((), dtype=torch.double))
+        G = torch.einsum("bin,bjn->bij", Cm, Bm)                                 # C B^T (one group)
+        y = torch.einsum("bij,bijh,bjh,bjhp->bihp", G, Lm, dt, x) + m.D[None, None, :, None] * x
+        y = y.reshape(Bsz, L, m.d_inner) * F.silu(z)
+        y = y * torch.rsqrt(y.pow(2).mean(-1, keepdim=True) + m.norm_eps) * m.norm.weight
+        got = m.out_proj(y)
+    # (the oracle carries its state in fp32 whatever the module's dtype: agreement to fp32 rounding)
+    assert torch.allclose(got, want, rtol=1e-5, atol=2e-6), float((got - want).abs().max())
