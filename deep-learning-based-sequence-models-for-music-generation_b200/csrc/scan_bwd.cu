@@ -66,7 +66,7 @@ struct BwdLayout {
 };
 
 template <typename T, int NPER, int NW, int kCK>
-__global__ void __launch_bounds__((NW + kBHelperWarps) * 32, 1) scan_bwd_kernel(const ScanBwdParams p) {
+__global__ void __launch_bounds__((NW + kBHelperWarps) * 32, (NPER == 4 && NW <= 4) ? 2 : 1) scan_bwd_kernel(const ScanBwdParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NPT = ((NW * NPER + 7) / 8) * 8;  // padded d_state of the shared tiles
