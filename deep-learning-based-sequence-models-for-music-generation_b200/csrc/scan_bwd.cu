@@ -61,7 +61,7 @@ struct BwdLayout {
     w_rB = o, o += kCK * NPT * 4;
     w_rC = o, o += kCK * NPT * 4;
     work_bytes = (o + 127) & ~127;
-    hs_bytes = (kCK / 2) * (NPER / 4) * NW * 32 * 16;  // even steps only, one float4 per 4 states and thread
+    hs_bytes = (kCK / 2) * NW * 32 * (NPER >= 4 ? (NPER / 4) * 16 : 8);  // even steps only: one float4 per 4 states and thread (NPER 2: one float2)
   }
 };
 
@@ -89,7 +89,9 @@ __global__ void __launch_bounds__((NW + kBHelperWarps) * 32, (NPER == 4 && NW <=
     // Per-channel operands (delta, delta*u, dy) are then ONE 4-byte shared load per lane (a single wavefront per
     // warp instead of four for a 16-byte load), B / C are full-warp broadcasts, sums over states stay inside the
     // thread, and only the sums over channels (dB, dC) cross lanes.
-    constexpr int NQ = NPER / 4;   // float4 groups of states per thread
+    constexpr int NQ = NPER / 4;   // float4 groups of states per thread (0 when the thread owns one state pair)
+    constexpr int NQ1 = NQ > 0 ? NQ : 1;
+    constexpr bool kPair = NPER == 2;
     constexpr int NP = NPER / 2;   // state pairs per thread
     const int n0 = warp * NPER;    // first state of this thread
     const int d = d0 + lane;
@@ -106,6 +108,12 @@ __global__ void __launch_bounds__((NW + kBHelperWarps) * 32, (NPER == 4 && NW <=
     // checkpoint layout [B][nck][ceil(N/4)][D][4] (scan_fwd.cu): 16 bytes per lane, 512 contiguous bytes per warp
     const int N4 = (p.N + 3) >> 2;
     auto load_ckpt = [&](int c, float2 (&h)[NP]) {
+      if constexpr (kPair) {   // half of a 16-byte checkpoint group
+        float2 v = make_float2(0.f, 0.f);
+        if (c > 0 && d < p.D && n0 < p.N)
+          v = __ldg(reinterpret_cast<const float2*>(reinterpret_cast<const float4*>(p.ckpt) + (((int64_t)b * nck + c) * N4 + (n0 >> 2)) * p.D + d) + ((n0 >> 1) & 1));
+        h[0] = v;
+      }
 #pragma unroll
       for (int q = 0; q < NQ; ++q) {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -117,6 +125,7 @@ __global__ void __launch_bounds__((NW + kBHelperWarps) * 32, (NPER == 4 && NW <=
     float2 hnext[NP];
     load_ckpt(nck - 1, hnext);
     float4* const hst = hs + tid;  // + (tp * NQ + q) * nscan_threads
+    float2* const hst2 = reinterpret_cast<float2*>(hs) + tid;  // NPER 2: + tp * nscan_threads
 
     int rslot = 0;
     for (int it = 0; it < nck; ++it) {
@@ -146,6 +155,13 @@ __global__ void __launch_bounds__((NW + kBHelperWarps) * 32, (NPER == 4 && NW <=
       for (int t = 0; t < kCK; ++t) {
         const float dl = wdl[t * kBD], du = wdu[t * kBD];
         const float2 dl2 = make_float2(dl, dl), du2 = make_float2(du, du);
+        if constexpr (kPair) {
+          const float2 b2 = *reinterpret_cast<const float2*>(Bf + t * NPT);
+          const float2 g0 = __fmul2_rn(dl2, A2[0]);
+          const float2 a0 = make_float2(ex2_approx(g0.x), ex2_approx(g0.y));
+          h[0] = __ffma2_rn(a0, h[0], __fmul2_rn(du2, b2));
+          if ((t & 1) == 0) hst2[(t >> 1) * nscan_threads] = h[0];
+        }
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
           const float4 b4 = *reinterpret_cast<const float4*>(Bf + t * NPT + 4 * q);
@@ -169,13 +185,17 @@ __global__ void __launch_bounds__((NW + kBHelperWarps) * 32, (NPER == 4 && NW <=
       // disambiguate) and can overlap the first step's arithmetic.
       struct RevOps {
         float dl, du, dy;
-        float4 B[NQ], C[NQ];
+        float4 B[NQ1], C[NQ1];   // (NPER 2: the pair sits in .x, .y)
       };
       struct RevOut {
         float g, S, red;
       };
       auto rev_load = [&](const int t, RevOps& o) {
         o.dl = wdl[t * kBD], o.du = wdu[t * kBD], o.dy = wdy[t * kBD];
+        if constexpr (kPair) {
+          const float2 b2 = *reinterpret_cast<const float2*>(Bf + t * NPT), c2 = *reinterpret_cast<const float2*>(Cf + t * NPT);
+          o.B[0] = make_float4(b2.x, b2.y, 0.f, 0.f), o.C[0] = make_float4(c2.x, c2.y, 0.f, 0.f);
+        }
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
           o.B[q] = *reinterpret_cast<const float4*>(Bf + t * NPT + 4 * q);
@@ -188,11 +208,11 @@ __global__ void __launch_bounds__((NW + kBHelperWarps) * 32, (NPER == 4 && NW <=
         float2 gs2 = make_float2(0.f, 0.f), S2 = make_float2(0.f, 0.f);
         float red[2 * NPER];  // dB_0..dB_{NPER-1}, dC_0..dC_{NPER-1} of this lane's channel
 #pragma unroll
-        for (int q = 0; q < NQ; ++q) {
+        for (int q = 0; q < NQ1; ++q) {
           const float2 Bp[2] = {make_float2(o.B[q].x, o.B[q].y), make_float2(o.B[q].z, o.B[q].w)};
           const float2 Cp[2] = {make_float2(o.C[q].x, o.C[q].y), make_float2(o.C[q].z, o.C[q].w)};
 #pragma unroll
-          for (int r = 0; r < 2; ++r) {
+          for (int r = 0; r < (kPair ? 1 : 2); ++r) {
             const int k = 2 * q + r;  // state pair index
             const float2 ga = __fmul2_rn(dl2, A2[k]);
             const float2 a = make_float2(ex2_approx(ga.x), ex2_approx(ga.y));
@@ -227,8 +247,8 @@ __global__ void __launch_bounds__((NW + kBHelperWarps) * 32, (NPER == 4 && NW <=
         reduce_scatter_step<(V >= 16 ? V / 16 : 1), 1>(red, lane & 1);
         out.red = red[0];
       };
-      // V = 32: every lane holds one value (index = lane); V = 16: index = lane >> 1; V = 8: index = lane >> 2
-      constexpr int SH = 2 * NPER >= 32 ? 0 : (2 * NPER == 16 ? 1 : 2);
+      // V = 32: every lane holds one value (index = lane); V = 16: index = lane >> 1; V = 8: lane >> 2; V = 4: lane >> 3
+      constexpr int SH = 2 * NPER >= 32 ? 0 : (2 * NPER == 16 ? 1 : (2 * NPER == 8 ? 2 : 3));
       const int ridx = lane >> SH;
       const bool rwriter = (lane & ((1 << SH) - 1)) == 0;
       float* const rdst = (ridx >= NPER ? redC : redB) + (ridx % NPER);
@@ -240,6 +260,7 @@ __global__ void __launch_bounds__((NW + kBHelperWarps) * 32, (NPER == 4 && NW <=
 #pragma unroll 1
       for (int tp = kCK / 2 - 1; tp >= 0; --tp) {
         float2 he[NP];
+        if constexpr (kPair) he[0] = hst2[tp * nscan_threads];
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
           const float4 h4 = hst[(tp * NQ + q) * nscan_threads];
@@ -683,11 +704,12 @@ static int bwd_dispatch(ScanBwdParams& p, int nper, cudaStream_t stream) {
   p.NW = p.NW <= 2 ? p.NW : (p.NW <= 4 ? 4 : 8);  // instantiated warp counts
   p.NPT = (p.NW * nper + 7) & ~7;
   switch (nper) {
+    case 2: return bwd_dispatch_ck<T, 2>(p, stream);
     case 4: return bwd_dispatch_ck<T, 4>(p, stream);
     case 8: return bwd_dispatch_ck<T, 8>(p, stream);
     case 16: return bwd_dispatch_ck<T, 16>(p, stream);
   }
-  return set_error(MAMBA_EINVAL, "scan_bwd: variant must be 0, 1, 4, 8 or 16 (got %d)", nper);
+  return set_error(MAMBA_EINVAL, "scan_bwd: variant must be 0, 1, 2, 4, 8 or 16 (got %d)", nper);
 }
 
 static bool bvec_ok(const void* ptr, int64_t bs, int64_t ls, size_t elt) {
@@ -761,8 +783,9 @@ extern "C" int mamba_scan_bwd(const MambaScanBwdArgs* a, void* stream) {
   p.vec_dz = a->dz ? bvec_ok(a->dz, a->dz_bs, a->dz_ls, elt) : 0;
   p.vec_ck = a->ckpt && aligned16(a->ckpt) && (p.D % 4 == 0);
 
-  // variant: 0 = auto, 1 = fused kernel with tensor-pipe channel reductions (d_state 32 / 64), 4 / 8 / 16 =
-  // lane<->channel kernel with that many states per thread
+  // variant: 0 = auto, 1 = fused kernel with tensor-pipe channel reductions (d_state 32 / 64), 2 / 4 / 8 / 16 =
+  // lane<->channel kernel with that many states per thread (2: d_state <= 16, eight scan warps; measured 1451 against
+  // 1491 us at config 5, B=2 — the four helper warps pace the CTA, not the scan warps — so auto keeps 4)
   int nper = a->variant;
   // auto: the fused kernel wins with bf16 I/O (plain tf32 column sums); with fp32 I/O its split-tf32 MMAs cost
   // more than the shuffles they replace

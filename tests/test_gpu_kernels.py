@@ -189,6 +189,34 @@ def test_scan_backward_variants_at_repo_d_state(variant, dtype, shape):
                      atol_abs=1e-6 if k == "A" else 0.0)
 
 
+@pytest.mark.parametrize("chunk", [8, 16])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(2, 100, 72, 16), (1, 41, 104, 8), (1, 1, 32, 16), (2, 17, 40, 16), (2, 333, 64, 16), (1, 50, 32, 4)])
+def test_scan_backward_one_state_pair_per_thread(chunk, dtype, shape):
+    """Backward variant 2 (lane<->channel kernel, one state PAIR per thread, d_state <= 16: eight scan warps per CTA
+    for shapes whose grid cannot fill the machine) against the oracle: every gradient, both checkpoint intervals."""
+    from mamba_b200 import ops
+    B, L, D, N = shape
+    t = scan_inputs(B, L, D, N, seed=21, dtype=dtype)
+    dout = torch.randn(B, L, D, generator=torch.Generator().manual_seed(6)).to(dtype)
+    c = _leafs(t, "cpu")
+    ref = _oracle_scan(c)
+    ref.backward(dout.float())
+    g = _leafs(t, "cuda")
+    rtol, floor = (RTOL32, 1e-5) if dtype == torch.float32 else (RTOL16, FLOOR16)
+    ops.SCAN_BWD_VARIANT = 2
+    try:
+        out = ops.selective_scan_fn(g["u"], g["delta_raw"], g["A"], g["B"], g["C"], g["D"], z=g["z"],
+                                    delta_bias=g["bias"], delta_softplus=True, chunk=chunk)
+        out.backward(dout.cuda())
+    finally:
+        ops.SCAN_BWD_VARIANT = 0
+    assert_close(out, ref, rtol, floor, what=f"fwd {dtype} {shape}")
+    for k in c:
+        assert_close(g[k].grad, c[k].grad, rtol, floor, what=f"scan bwd variant 2 {dtype} d{k} {shape} chunk {chunk}",
+                     atol_abs=1e-6 if k == "A" else 0.0)
+
+
 # TMA-staged forward (scan_fwd_tma.cu): variant 100 + 10*tiling + split.  Shapes: 16-byte aligned rows (the kernel's
 # eligibility rule), ragged in L and in the channel tile, every d_state bracket (<=16, <=32, <=64, <=128).
 @pytest.mark.parametrize("variant", [110, 120, 111, 121])
