@@ -65,8 +65,14 @@ struct BwdLayout {
   }
 };
 
-template <typename T, int NPER, int NW, int kCK>
-__global__ void __launch_bounds__((NW + kBHelperWarps) * 32, (NPER == 4 && NW <= 4) ? 2 : 1) scan_bwd_kernel(const ScanBwdParams p) {
+// HT = helper teams (of kBHelperWarps warps each).  With two teams the chunks alternate between them and every team
+// has TWO raw and TWO work slots of its own, so that a team's pre-pass of its next chunk is finished before the scan
+// warps are done with its current one: the per-(t, d) work then has two scan-chunks of time per chunk instead of one.
+// That is for small d_state (the scan warps' share per chunk shrinks with d_state, the helpers' does not) on grids
+// that cannot fill the machine (otherwise two resident CTAs per SM do the same job, see the launch bounds).
+template <typename T, int NPER, int NW, int kCK, int HT>
+__global__ void __launch_bounds__((NW + HT * kBHelperWarps) * 32, (NPER == 4 && NW <= 4 && HT == 1) ? 2 : 1)
+    scan_bwd_kernel(const ScanBwdParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NPT = ((NW * NPER + 7) / 8) * 8;  // padded d_state of the shared tiles
@@ -75,13 +81,17 @@ __global__ void __launch_bounds__((NW + kBHelperWarps) * 32, (NPER == 4 && NW <=
   const int dvalid = min(kBD, p.D - d0);
   const BwdLayout<T, kCK> lay(NW, NPT, NPER);
   unsigned char* const raw_base = smem;
-  unsigned char* const work_base = smem + (size_t)kBRing * lay.raw_bytes;
-  float4* const hs = reinterpret_cast<float4*>(work_base + (size_t)2 * lay.work_bytes);
+  constexpr int NSLOT = 2 * HT;   // raw slots = work slots; iteration i uses slot i % NSLOT (team i % HT)
+  static_assert(kBRing == 2, "slot = iteration % NSLOT assumes the two-deep raw ring per team");
+  unsigned char* const work_base = smem + (size_t)NSLOT * lay.raw_bytes;
+  float4* const hs = reinterpret_cast<float4*>(work_base + (size_t)NSLOT * lay.work_bytes);
   const int nck = p.nck;
   constexpr int nscan_threads = NW * 32;
-  constexpr int bar_count = nscan_threads + kBHelperThreads;
+  constexpr int bar_count = nscan_threads + kBHelperThreads;   // the scan warps + ONE helper team
   const bool has_z = p.flags & MAMBA_FLAG_HAS_Z;
-  // barrier ids: 1,2 = READY[work slot]; 3,4 = DONE[work slot]; 5 = helpers only.  Iteration i handles chunk nck-1-i.
+  // barrier ids: 1 + slot = READY[slot]; 1 + NSLOT + slot = DONE[slot]; 1 + 2*NSLOT + team = that team's helpers only;
+  // 15 = all helpers (epilogue).  Iteration i handles chunk nck-1-i.
+  constexpr int kBarReady = 1, kBarDone = 1 + NSLOT, kBarTeam = 1 + 2 * NSLOT, kBarHelpers = 15;
 
   if (warp < NW) {
     // ========================================= SCAN WARPS ===============================================
@@ -127,12 +137,11 @@ __global__ void __launch_bounds__((NW + kBHelperWarps) * 32, (NPER == 4 && NW <=
     float4* const hst = hs + tid;  // + (tp * NQ + q) * nscan_threads
     float2* const hst2 = reinterpret_cast<float2*>(hs) + tid;  // NPER 2: + tp * nscan_threads
 
-    int rslot = 0;
     for (int it = 0; it < nck; ++it) {
       const int c = nck - 1 - it;
-      const int ws = it & 1;
+      const int ws = it & (NSLOT - 1);
       unsigned char* wbase = work_base + (size_t)ws * lay.work_bytes;
-      unsigned char* rbase = raw_base + (size_t)rslot * lay.raw_bytes;
+      unsigned char* rbase = raw_base + (size_t)ws * lay.raw_bytes;
       const float* wdl = reinterpret_cast<const float*>(wbase + lay.w_dl) + lane;
       const float* wdu = reinterpret_cast<const float*>(wbase + lay.w_du) + lane;
       const float* wdy = reinterpret_cast<const float*>(wbase + lay.w_dy) + lane;
@@ -148,7 +157,7 @@ __global__ void __launch_bounds__((NW + kBHelperWarps) * 32, (NPER == 4 && NW <=
       float2 h[NP];
 #pragma unroll
       for (int q = 0; q < NP; ++q) h[q] = hnext[q];
-      bar_sync(1 + ws, bar_count);  // chunk c prepared
+      bar_sync(kBarReady + ws, bar_count);  // chunk c prepared
 
       // ---- forward recompute: h_t of the EVEN steps of the chunk -> shared memory --------------------------
 #pragma unroll 4
@@ -275,8 +284,7 @@ __global__ void __launch_bounds__((NW + kBHelperWarps) * 32, (NPER == 4 && NW <=
         rev_store(2 * tp + 1, r1);
         rev_store(2 * tp, r0);
       }
-      bar_arrive(3 + ws, bar_count);  // chunk c swept
-      rslot = (rslot + 1 == kBRing) ? 0 : rslot + 1;
+      bar_arrive(kBarDone + ws, bar_count);  // chunk c swept
     }
     // ---- epilogue: dA partial of this batch element -----------------------------------------------------------
     if (d < p.D) {
@@ -290,7 +298,8 @@ __global__ void __launch_bounds__((NW + kBHelperWarps) * 32, (NPER == 4 && NW <=
   }
 
   // =========================================== HELPER WARPS ===============================================
-  const int ht = tid - nscan_threads;  // 0..127
+  const int team = (tid - nscan_threads) / kBHelperThreads;   // 0 .. HT-1
+  const int ht = (tid - nscan_threads) % kBHelperThreads;     // 0..127 inside the team
   const bool do_softplus = p.flags & MAMBA_FLAG_DELTA_SOFTPLUS;
   const int my_t = ht >> 3, my_c = 4 * (ht & 7);  // this thread's (timestep, 4 channels) of every chunk
   const bool my_row = my_t < kCK;                  // with 8-step chunks half of the helper threads only load
@@ -339,7 +348,7 @@ __global__ void __launch_bounds__((NW + kBHelperWarps) * 32, (NPER == 4 && NW <=
   auto pre_pass = [&](int it, int rslot) {
     const int c = nck - 1 - it;
     unsigned char* rbase = raw_base + (size_t)rslot * lay.raw_bytes;
-    unsigned char* wbase = work_base + (size_t)(it & 1) * lay.work_bytes;
+    unsigned char* wbase = work_base + (size_t)(it & (NSLOT - 1)) * lay.work_bytes;
     const int rv = min(kCK, p.L - c * kCK);
     const int o = my_t * kBD + my_c;
     if (my_row) {
@@ -390,7 +399,7 @@ __global__ void __launch_bounds__((NW + kBHelperWarps) * 32, (NPER == 4 && NW <=
   auto post_pass = [&](int it, int rslot) {
     const int c = nck - 1 - it;
     unsigned char* rbase = raw_base + (size_t)rslot * lay.raw_bytes;
-    unsigned char* wbase = work_base + (size_t)(it & 1) * lay.work_bytes;
+    unsigned char* wbase = work_base + (size_t)(it & (NSLOT - 1)) * lay.work_bytes;
     const int t0 = c * kCK;
     const int rv = min(kCK, p.L - t0);
     if (my_row && my_t < rv) {
@@ -461,34 +470,61 @@ __global__ void __launch_bounds__((NW + kBHelperWarps) * 32, (NPER == 4 && NW <=
     }
   };
 
-  // prologue
-  for (int it = 0; it < kBRing - 1; ++it) issue_loads(it, it);
-  int rslot = 0, pslot = kBRing - 1;
-  for (int it = 0; it < nck; ++it) {
-    cp_async_wait<kBRing - 2>();
-    bar_sync(5, kBHelperThreads);
-    pre_pass(it, rslot);
-    bar_arrive(1 + (it & 1), bar_count);  // READY
-    if (it >= 1) {
-      bar_sync(3 + ((it - 1) & 1), bar_count);  // DONE of the previous chunk
-      post_pass(it - 1, pslot);
+  if constexpr (HT == 1) {
+    // prologue
+    for (int it = 0; it < kBRing - 1; ++it) issue_loads(it, it);
+    int rslot = 0, pslot = kBRing - 1;
+    for (int it = 0; it < nck; ++it) {
+      cp_async_wait<kBRing - 2>();
+      bar_sync(kBarTeam, kBHelperThreads);
+      pre_pass(it, rslot);
+      bar_arrive(kBarReady + (it & 1), bar_count);  // READY
+      if (it >= 1) {
+        bar_sync(kBarDone + ((it - 1) & 1), bar_count);  // DONE of the previous chunk
+        post_pass(it - 1, pslot);
+      }
+      bar_sync(kBarTeam, kBHelperThreads);
+      issue_loads(it + kBRing - 1, pslot);
+      pslot = rslot;
+      rslot = (rslot + 1 == kBRing) ? 0 : rslot + 1;
     }
-    bar_sync(5, kBHelperThreads);
-    issue_loads(it + kBRing - 1, pslot);
-    pslot = rslot;
-    rslot = (rslot + 1 == kBRing) ? 0 : rslot + 1;
+    bar_sync(kBarDone + ((nck - 1) & 1), bar_count);
+    post_pass(nck - 1, pslot);
+  } else {
+    // team t owns iterations t, t + HT, ... and slots t, t + HT (raw and work alike: slot = iteration % NSLOT)
+    const int bt = kBarTeam + team;
+    issue_loads(team, team);                       // (an empty group when there is no such chunk)
+    issue_loads(team + HT, team + HT);
+    if (team < nck) {
+      cp_async_wait<1>();
+      bar_sync(bt, kBHelperThreads);
+      pre_pass(team, team);
+      bar_arrive(kBarReady + team, bar_count);
+    }
+    for (int it = team; it < nck; it += HT) {
+      const int slot = it & (NSLOT - 1), nxt = it + HT;
+      if (nxt < nck) {   // the team's next chunk is prepared BEFORE it waits for the scan warps to finish this one
+        cp_async_wait<0>();
+        bar_sync(bt, kBHelperThreads);
+        pre_pass(nxt, nxt & (NSLOT - 1));
+        bar_arrive(kBarReady + (nxt & (NSLOT - 1)), bar_count);
+      }
+      bar_sync(kBarDone + slot, bar_count);
+      post_pass(it, slot);
+      bar_sync(bt, kBHelperThreads);           // every thread of the team is done with the raw slot
+      issue_loads(it + 2 * HT, slot);
+    }
   }
-  bar_sync(3 + ((nck - 1) & 1), bar_count);
-  post_pass(nck - 1, pslot);
 
   // ---- dD / d_bias: sum this CTA's 16 timestep-rows in shared memory, one partial per (b, d) ------------------
-  bar_sync(5, kBHelperThreads);
-  float* fin = reinterpret_cast<float*>(work_base);  // [2][16][32], the work slots are free now
-  constexpr int kRows = kBHelperThreads / 8;
-  *reinterpret_cast<float4*>(fin + my_t * kBD + my_c) = make_float4(dD_acc[0], dD_acc[1], dD_acc[2], dD_acc[3]);
-  *reinterpret_cast<float4*>(fin + (kRows + my_t) * kBD + my_c) = make_float4(db_acc[0], db_acc[1], db_acc[2], db_acc[3]);
-  bar_sync(5, kBHelperThreads);
-  if (ht < kBD && d0 + ht < p.D) {
+  bar_sync(kBarHelpers, HT * kBHelperThreads);
+  float* fin = reinterpret_cast<float*>(work_base);  // [2][HT * 16][32], the work slots are free now
+  constexpr int kRows = HT * kBHelperThreads / 8;
+  const int my_r = team * (kBHelperThreads / 8) + my_t;
+  *reinterpret_cast<float4*>(fin + my_r * kBD + my_c) = make_float4(dD_acc[0], dD_acc[1], dD_acc[2], dD_acc[3]);
+  *reinterpret_cast<float4*>(fin + (kRows + my_r) * kBD + my_c) = make_float4(db_acc[0], db_acc[1], db_acc[2], db_acc[3]);
+  bar_sync(kBarHelpers, HT * kBHelperThreads);
+  if (team == 0 && ht < kBD && d0 + ht < p.D) {
     float sD = 0.f, sb = 0.f;
     for (int r = 0; r < kRows; ++r) {
       sD += fin[r * kBD + ht];
@@ -614,9 +650,9 @@ __global__ void scan_bwd_finalize_kernel(const ScanBwdParams p, int rows_per_blo
 }
 
 template <typename T, int kCK>
-static size_t bwd_smem_bytes(int NW, int NPT, int NPER) {
+static size_t bwd_smem_bytes(int NW, int NPT, int NPER, int HT) {
   const BwdLayout<T, kCK> lay(NW, NPT, NPER);
-  return (size_t)kBRing * lay.raw_bytes + (size_t)2 * lay.work_bytes + lay.hs_bytes;
+  return (size_t)2 * HT * lay.raw_bytes + (size_t)2 * HT * lay.work_bytes + lay.hs_bytes;
 }
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -636,16 +672,16 @@ static size_t bwd_workspace_layout(int B, int L, int D, int N, size_t* o_dB, siz
 template <typename T>
 static int launch_finalize(const ScanBwdParams& p, cudaStream_t stream);
 
-template <typename T, int NPER, int NW, int kCK>
+template <typename T, int NPER, int NW, int kCK, int HT = 1>
 static int launch_bwd(const ScanBwdParams& p, cudaStream_t stream) {
-  const size_t smem = bwd_smem_bytes<T, kCK>(NW, p.NPT, NPER);
+  const size_t smem = bwd_smem_bytes<T, kCK>(NW, p.NPT, NPER, HT);
   if (smem > 227 * 1024)
     return set_error(MAMBA_ESIZE, "scan_bwd: d_state %d needs %zu B of shared memory", p.N, smem);
-  auto kern = scan_bwd_kernel<T, NPER, NW, kCK>;
+  auto kern = scan_bwd_kernel<T, NPER, NW, kCK, HT>;
   static thread_local SmemConfig cfg;
   if (int rc = ensure_dynamic_smem(kern, smem, cfg, "scan_bwd")) return rc;
   dim3 grid(p.ntiles, p.B);
-  kern<<<grid, (NW + kBHelperWarps) * 32, smem, stream>>>(p);
+  kern<<<grid, (NW + HT * kBHelperWarps) * 32, smem, stream>>>(p);
   count_launch();
   int rc = check_launch("scan_bwd");
   if (rc) return rc;
@@ -675,6 +711,8 @@ static int bwd_dispatch_nw(const ScanBwdParams& p, cudaStream_t stream) {
 
 template <typename T, int NPER>
 static int bwd_dispatch_ck(const ScanBwdParams& p, cudaStream_t stream) {
+  if (NPER == 4 && p.helper_teams == 2 && p.NW == 4)   // d_state 16, four scan warps + two helper teams
+    return p.ck == 8 ? launch_bwd<T, 4, 4, 8, 2>(p, stream) : launch_bwd<T, 4, 4, 16, 2>(p, stream);
   return p.ck == 8 ? bwd_dispatch_nw<T, NPER, 8>(p, stream) : bwd_dispatch_nw<T, NPER, 16>(p, stream);
 }
 
@@ -709,7 +747,7 @@ static int bwd_dispatch(ScanBwdParams& p, int nper, cudaStream_t stream) {
     case 8: return bwd_dispatch_ck<T, 8>(p, stream);
     case 16: return bwd_dispatch_ck<T, 16>(p, stream);
   }
-  return set_error(MAMBA_EINVAL, "scan_bwd: variant must be 0, 1, 2, 4, 8 or 16 (got %d)", nper);
+  return set_error(MAMBA_EINVAL, "scan_bwd: variant must be 0, 1, 2, 4, 8, 16 or 104 (got %d)", nper);
 }
 
 static bool bvec_ok(const void* ptr, int64_t bs, int64_t ls, size_t elt) {
@@ -787,10 +825,17 @@ extern "C" int mamba_scan_bwd(const MambaScanBwdArgs* a, void* stream) {
   // lane<->channel kernel with that many states per thread (2: d_state <= 16, eight scan warps; measured 1451 against
   // 1491 us at config 5, B=2 — the four helper warps pace the CTA, not the scan warps — so auto keeps 4)
   int nper = a->variant;
+  // 104: the 4-states-per-thread kernel with TWO helper teams (d_state 9..16).  Auto picks it when the grid is a single
+  // wave of one CTA per SM (the second team then does what a second resident CTA's helpers would do)
+  p.helper_teams = 1;
+  if (nper == 104) nper = 4, p.helper_teams = 2;
   // auto: the fused kernel wins with bf16 I/O (plain tf32 column sums); with fp32 I/O its split-tf32 MMAs cost
   // more than the shuffles they replace
   if (nper == 0) nper = ((p.N == 64 || p.N == 32) && a->dtype == MAMBA_BF16) ? 1 : (p.N <= 32 ? 4 : 8);
   while (nper > 1 && nper < 16 && ceil_div(p.N, nper) > kBMaxWarps) nper *= 2;
+  if (a->variant == 0 && nper == 4 && p.N > 8 && p.N <= 16 && (int64_t)p.ntiles * p.B <= kNumSMs) p.helper_teams = 2;
+  if (p.helper_teams == 2 && !(nper == 4 && p.N > 8 && p.N <= 16))
+    return set_error(MAMBA_EINVAL, "scan_bwd: variant 104 (two helper teams) needs d_state 9..16 (got %d)", p.N);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   return a->dtype == MAMBA_F32 ? bwd_dispatch<float>(p, nper, st) : bwd_dispatch<__nv_bfloat16>(p, nper, st);
 }

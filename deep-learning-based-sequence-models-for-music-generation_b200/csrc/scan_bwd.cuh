@@ -12,7 +12,7 @@ constexpr int kBMaxWarps = 8;  // scan warps per CTA
 constexpr int kBRing = 2;      // raw-tile ring depth (a chunk is >= 2 us of work at d_state 64)
 
 struct ScanBwdParams {
-  int B, L, D, N, NW, NPT, nck, ck, flags, ntiles;
+  int B, L, D, N, NW, NPT, nck, ck, flags, ntiles, helper_teams;
   const void *u, *delta, *Bm, *Cm, *z, *dout, *ypre;
   int64_t u_bs, u_ls, delta_bs, delta_ls, B_bs, B_ls, C_bs, C_ls, z_bs, z_ls, dout_bs, dout_ls, ypre_bs, ypre_ls;
   void *du, *ddelta, *dz, *dB, *dC;

@@ -117,7 +117,7 @@ typedef struct MambaScanBwdArgs {
   int32_t flags;
   int32_t variant;   /* 0 = auto; 1 = fused recompute/reverse kernel with tensor-pipe channel sums (d_state 32 or 64;
                         auto for bf16 I/O); 2 / 4 / 8 / 16 = lane<->channel kernel with that many states per thread
-                        (2: d_state <= 16) */
+                        (2: d_state <= 16); 104 = 4 states per thread with two helper-warp teams (d_state 9..16) */
   int32_t reserved;
   const void* u;     int64_t u_bs, u_ls;
   const void* delta; int64_t delta_bs, delta_ls;

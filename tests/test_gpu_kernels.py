@@ -189,14 +189,19 @@ def test_scan_backward_variants_at_repo_d_state(variant, dtype, shape):
                      atol_abs=1e-6 if k == "A" else 0.0)
 
 
+@pytest.mark.parametrize("variant", [2, 104, 4])
 @pytest.mark.parametrize("chunk", [8, 16])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("shape", [(2, 100, 72, 16), (1, 41, 104, 8), (1, 1, 32, 16), (2, 17, 40, 16), (2, 333, 64, 16), (1, 50, 32, 4)])
-def test_scan_backward_one_state_pair_per_thread(chunk, dtype, shape):
-    """Backward variant 2 (lane<->channel kernel, one state PAIR per thread, d_state <= 16: eight scan warps per CTA
-    for shapes whose grid cannot fill the machine) against the oracle: every gradient, both checkpoint intervals."""
+@pytest.mark.parametrize("shape", [(2, 100, 72, 16), (1, 41, 104, 8), (1, 1, 32, 16), (2, 17, 40, 16), (2, 333, 64, 16), (1, 50, 32, 4),
+                                   (1, 64, 32, 12), (2, 129, 32, 16)])
+def test_scan_backward_small_d_state_variants(variant, chunk, dtype, shape):
+    """Backward variants for small d_state against the oracle, every gradient, both checkpoint intervals, 1..21 chunks:
+    2 = one state PAIR per thread (eight scan warps), 104 = four states per thread with TWO helper teams (d_state
+    9..16; the default when the grid is a single wave), 4 = four states per thread, one team (two CTAs per SM)."""
     from mamba_b200 import ops
     B, L, D, N = shape
+    if variant == 104 and not 8 < N <= 16:
+        pytest.skip("two helper teams: d_state 9..16")
     t = scan_inputs(B, L, D, N, seed=21, dtype=dtype)
     dout = torch.randn(B, L, D, generator=torch.Generator().manual_seed(6)).to(dtype)
     c = _leafs(t, "cpu")
@@ -204,7 +209,7 @@ def test_scan_backward_one_state_pair_per_thread(chunk, dtype, shape):
     ref.backward(dout.float())
     g = _leafs(t, "cuda")
     rtol, floor = (RTOL32, 1e-5) if dtype == torch.float32 else (RTOL16, FLOOR16)
-    ops.SCAN_BWD_VARIANT = 2
+    ops.SCAN_BWD_VARIANT = variant
     try:
         out = ops.selective_scan_fn(g["u"], g["delta_raw"], g["A"], g["B"], g["C"], g["D"], z=g["z"],
                                     delta_bias=g["bias"], delta_softplus=True, chunk=chunk)
@@ -213,7 +218,7 @@ def test_scan_backward_one_state_pair_per_thread(chunk, dtype, shape):
         ops.SCAN_BWD_VARIANT = 0
     assert_close(out, ref, rtol, floor, what=f"fwd {dtype} {shape}")
     for k in c:
-        assert_close(g[k].grad, c[k].grad, rtol, floor, what=f"scan bwd variant 2 {dtype} d{k} {shape} chunk {chunk}",
+        assert_close(g[k].grad, c[k].grad, rtol, floor, what=f"scan bwd variant {variant} {dtype} d{k} {shape} chunk {chunk}",
                      atol_abs=1e-6 if k == "A" else 0.0)
 
 
