@@ -304,7 +304,9 @@ class Trainer:
             seen = {id(p) for g in groups for p in g}
             groups[-1] = groups[-1] + [p for p in model.norm_f.parameters() if id(p) not in seen]
             seen |= {id(p) for p in model.norm_f.parameters()}
-            groups.append([p for p in model.parameters() if id(p) not in seen])
+            rest = [p for p in model.parameters() if id(p) not in seen]
+            if any(p.requires_grad for p in rest):
+                groups.append(rest)
             self._stage_params = [[p for p in g if p.requires_grad] for g in groups]
         # DDP broadcasts rank 0's parameters and buffers at construction (train_parallel.py:151); do the same, so that
         # ranks that seeded differently (or loaded different checkpoints) cannot apply averaged gradients to
@@ -460,7 +462,8 @@ class Trainer:
             self._finish_stage(gi)
         if emb_in is not emb:
             torch.autograd.backward([emb], [emb_in.grad])
-        self._finish_stage(len(groups))
+        if len(self._stage_params) > len(groups):   # the embedding / tied-head stage
+            self._finish_stage(len(groups))
         if self._stage_optimizers is None:
             self.grads.finish()
             self.optimizer.step()
